@@ -1,0 +1,189 @@
+/*
+ * nprsph.h -- C ABI of libnprsph.so, the B200-native drop-in for NPR-SPH's SPH step.
+ *
+ * The reference has no FFI: its SPH path sits behind an implicit OpenGL-object contract
+ * inside one process.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference repo's NPR-SPH/).
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Rules that mirror the reference:
+ *   - one caller thread per context (same rule as the GL context thread, Main.cpp:680);
+ *   - the simulation starts PAUSED (`bool simulate;` zero-initialised, Main.cpp:87) and
+ *     nprsph_step() is a no-op while paused (Main.cpp:293);
+ *   - parameter edits take effect at the next step (sendUniforms, Main.cpp:274-278,314);
+ *   - nprsph_reset() restores the initial block and keeps the pause flag and the
+ *     constants (keyboard 'r', Main.cpp:460-464);
+ *   - every function returns 0 on success or a negative nprsph_status; no exceptions.
+ * There is no CPU fallback: creating a context without a CUDA device fails.
+ */
+#ifndef NPRSPH_H
+#define NPRSPH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPRSPH_ABI_VERSION 1
+
+typedef enum nprsph_status {
+    NPRSPH_OK = 0,
+    NPRSPH_ERR_INVALID = -1,      /* bad argument */
+    NPRSPH_ERR_CUDA = -2,         /* CUDA runtime error (sticky, see nprsph_last_error) */
+    NPRSPH_ERR_NOMEM = -3,
+    NPRSPH_ERR_STATE = -4,        /* call not valid in the current state */
+    NPRSPH_ERR_UNSUPPORTED = -5,  /* e.g. GL interop without a current GL context */
+    NPRSPH_ERR_COMM = -6          /* multi-GPU exchange failed */
+} nprsph_status;
+
+/* struct Particle -- Main.cpp:93-99; rho_pres_comp.glsl:12-18 (std430, stride 64 B).
+ * extras[0] = rho, extras[1] = pressure, extras[2] ("age") and every .w lane are never
+ * written by the passes and are preserved from upload to download. */
+typedef struct nprsph_particle {
+    float pos[4];
+    float vel[4];
+    float force[4];
+    float extras[4];
+} nprsph_particle;
+
+/* ConstantsUniform -- Main.cpp:110-116; rho_pres_comp.glsl:25-31 (std140, binding 1, 16 B) */
+typedef struct nprsph_constants {
+    float mass;             /* 0.02   */
+    float smoothing_coeff;  /* 4.0 ; h = smoothing_coeff * particle_radius */
+    float visc;             /* 3000   */
+    float resting_rho;      /* 1000   */
+} nprsph_constants;
+
+/* BoundaryUniform -- Main.cpp:118-122; integrate_comp.glsl:27-31 (binding 2, 32 B, upper first) */
+typedef struct nprsph_boundary {
+    float upper[4];         /* ( 0.5,  1.0,   0.5, 1) */
+    float lower[4];         /* (-0.1, -0.35, -0.1, 1) */
+} nprsph_boundary;
+
+/* What the reference bakes in at compile time (Main.cpp:33-36 and the shader consts),
+ * plus the knobs of the new grid pipeline.  Fill with nprsph_config_default() first. */
+typedef struct nprsph_config {
+    uint32_t struct_size;       /* = sizeof(nprsph_config) */
+    int32_t  device;            /* CUDA device ordinal */
+    void*    stream;            /* caller's cudaStream_t to run on; NULL = library-owned */
+    float    particle_radius;   /* PARTICLE_RADIUS 0.005f, rho_pres_comp.glsl:5   */
+    float    gas_const;         /* GAS_CONST 2000,        rho_pres_comp.glsl:33  */
+    float    gravity[3];        /* G (0,-9806.65,0),      force_comp.glsl:33     */
+    float    damping;           /* DAMPING 0.3,           integrate_comp.glsl:8  */
+    float    dt;                /* 1.0f/NUM_PARTICLES = 1e-4, integrate_comp.glsl:33 */
+    float    pi;                /* PI 3.141592741f,       rho_pres_comp.glsl:8   */
+    int32_t  cell_subdiv;       /* grid cell = h/cell_subdiv (1 or 2); 0 = default */
+    uint32_t max_cells;         /* cap on the cell table; 0 = default (2^28)      */
+    uint32_t flags;             /* NPRSPH_FLAG_* */
+    uint32_t reserved;
+} nprsph_config;
+
+#define NPRSPH_FLAG_COUNT_NEIGHBOURS 1u  /* passes also record per-particle neighbour counts */
+
+typedef struct nprsph_stats {
+    uint64_t num_particles;
+    uint64_t steps_done;
+    uint64_t nan_particles;     /* particles whose position has a NaN component */
+    uint32_t num_cells;
+    uint32_t grid_dim[3];
+    uint32_t key_bits;
+    uint32_t sort_passes;
+    float    cell_size;
+    float    smoothing_length;
+    int32_t  paused;
+    int32_t  cell_subdiv;
+} nprsph_stats;
+
+/* stage indices for nprsph_profile_step() */
+enum {
+    NPRSPH_STAGE_KEYS = 0,      /* stand-alone key kernel (only when keys are stale) */
+    NPRSPH_STAGE_SORT,          /* histogram + onesweep digit passes */
+    NPRSPH_STAGE_CELLS,         /* cell-start table */
+    NPRSPH_STAGE_REORDER,       /* gather pos/vel into cell order */
+    NPRSPH_STAGE_RHO,           /* rho_pres_comp.glsl */
+    NPRSPH_STAGE_FORCE,         /* force_comp.glsl */
+    NPRSPH_STAGE_INTEGRATE,     /* integrate_comp.glsl (+ next-step keys) */
+    NPRSPH_NUM_STAGES
+};
+
+/* items for nprsph_debug_read() (parity tests) */
+enum {
+    NPRSPH_DBG_SORTED_KEYS = 0, /* uint32[n]: cell key of the particle in slot s            */
+    NPRSPH_DBG_SLOT_IDS,        /* uint32[n]: original particle index held in slot s        */
+    NPRSPH_DBG_CELL_START,      /* uint32[num_cells+2]: first slot with key >= c            */
+    NPRSPH_DBG_COUNTS_RHO,      /* uint32[n] by original index; needs FLAG_COUNT_NEIGHBOURS */
+    NPRSPH_DBG_COUNTS_FORCE,    /* uint32[n] by original index                              */
+    NPRSPH_DBG_LAST_PERM        /* uint32[n]: previous slot of the particle now in slot s   */
+};
+
+typedef struct nprsph_ctx nprsph_ctx;
+
+/* ---- lifetime (replaces the process-global GL objects, Main.cpp:42-56,524-538) -------- */
+int  nprsph_abi_version(void);
+void nprsph_config_default(nprsph_config* cfg);
+int  nprsph_create(const nprsph_config* cfg, nprsph_ctx** out);
+int  nprsph_destroy(nprsph_ctx* ctx);
+const char* nprsph_last_error(const nprsph_ctx* ctx);   /* ctx may be NULL: create errors */
+
+/* ---- parameters (glBufferSubData of the two UBOs, Main.cpp:274-278) ------------------- */
+int nprsph_set_constants(nprsph_ctx* ctx, const nprsph_constants* c);
+int nprsph_get_constants(const nprsph_ctx* ctx, nprsph_constants* c);
+int nprsph_set_boundary(nprsph_ctx* ctx, const nprsph_boundary* b);
+int nprsph_get_boundary(const nprsph_ctx* ctx, nprsph_boundary* b);
+/* run-time version of editing the shader consts + 'r' hot reload (Main.cpp:428-450) */
+int nprsph_set_config(nprsph_ctx* ctx, const nprsph_config* cfg);
+int nprsph_get_config(const nprsph_ctx* ctx, nprsph_config* cfg);
+
+/* ---- particle buffer (SSBO binding 0, Main.cpp:524-527) -------------------------------- */
+/* make_grid()+init_particles(), Main.cpp:488-521: nx*ny*nz block, x outermost, z innermost,
+ * pos = origin + (i,j,k)*spacing, w = 1, everything else 0.  jitter > 0 adds a seeded
+ * +-jitter offset per coordinate (synthetic dam-break scenes).  Defines what reset restores. */
+int nprsph_scene_block(nprsph_ctx* ctx, int nx, int ny, int nz, float spacing,
+                       const float origin[3], float jitter, uint32_t seed);
+/* glBufferData(..., particles.data(), ...) -- Main.cpp:526 */
+int nprsph_upload_particles(nprsph_ctx* ctx, const nprsph_particle* host, uint64_t n);
+/* new (the reference never reads back): records come back in ORIGINAL particle order */
+int nprsph_download_particles(nprsph_ctx* ctx, nprsph_particle* host, uint64_t n);
+/* device pointer to the 64-B record array in original order (what SSBO binding 0 holds);
+ * valid until the next call that changes n; brought up to date by this call */
+int nprsph_device_particles(nprsph_ctx* ctx, void** device_ptr, uint64_t* n);
+uint64_t nprsph_num_particles(const nprsph_ctx* ctx);
+
+/* ---- pause / reset (keyboard(), Main.cpp:454-476) ---------------------------------------- */
+int nprsph_set_paused(nprsph_ctx* ctx, int paused);
+int nprsph_toggle_pause(nprsph_ctx* ctx);       /* 'p' */
+int nprsph_is_paused(const nprsph_ctx* ctx);
+int nprsph_reset(nprsph_ctx* ctx);              /* 'r' */
+
+/* ---- stepping (display() compute block, Main.cpp:291-305) -------------------------------- */
+int nprsph_step(nprsph_ctx* ctx, int n_steps);  /* async; no-op while paused */
+int nprsph_sync(nprsph_ctx* ctx);
+/* one pass at a time, regardless of the pause flag (glDispatchCompute of one program):
+ * rho_pres_comp.glsl / force_comp.glsl / integrate_comp.glsl */
+int nprsph_pass_rho(nprsph_ctx* ctx);
+int nprsph_pass_force(nprsph_ctx* ctx);
+int nprsph_pass_integrate(nprsph_ctx* ctx);
+void* nprsph_stream(const nprsph_ctx* ctx);     /* cudaStream_t the work is queued on */
+
+/* ---- measurement / introspection ---------------------------------------------------------- */
+int nprsph_get_stats(nprsph_ctx* ctx, nprsph_stats* out);
+/* runs n_steps (ignores pause) with CUDA events around each stage on the context's stream;
+ * stage_ms[NPRSPH_NUM_STAGES] receives the mean ms per step of each stage */
+int nprsph_profile_step(nprsph_ctx* ctx, int n_steps, float* stage_ms);
+int nprsph_debug_read(nprsph_ctx* ctx, int item, void* host_dst, uint64_t bytes);
+/* stand-alone run of the onesweep sort on host arrays (tests): stable, low key_bits bits */
+int nprsph_sort_pairs_host(int device, const uint32_t* keys_in, const uint32_t* vals_in,
+                           uint64_t n, int key_bits, uint32_t* keys_out, uint32_t* vals_out);
+
+/* ---- OpenGL presenter (VAO attr 0 on the SSBO, Main.cpp:529-535) --------------------------- */
+/* Registers the caller's GL buffer (>= n*64 B) through CUDA-GL interop; publish copies the
+ * current records into it.  Need a current GL context; headless callers never call these. */
+int nprsph_gl_register(nprsph_ctx* ctx, unsigned int gl_buffer);
+int nprsph_gl_publish(nprsph_ctx* ctx);
+int nprsph_gl_unregister(nprsph_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPRSPH_H */

@@ -1,0 +1,773 @@
+// api.cu -- host runtime and C ABI of libnprsph.so (include/nprsph.h).
+//
+// Replaces the SPH-driver part of the reference's Main.cpp: particle/UBO creation
+// (Main.cpp:510-539,631-641), the per-frame dispatch block (Main.cpp:291-305), parameter
+// upload (Main.cpp:274-278) and the p/r keys (Main.cpp:454-476).  Everything runs on one CUDA
+// stream; there is no CPU implementation of any pass behind this API.
+#include "../../include/nprsph.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "kernels.cuh"
+#include "sort.cuh"
+
+using namespace nprsph;
+
+// CUDA-GL interop entry points of the CUDA runtime, declared by hand because this image has
+// no <GL/gl.h> for cuda_gl_interop.h to include.
+extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource** resource,
+                                                    unsigned int buffer, unsigned int flags);
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct nprsph_ctx {
+    nprsph_config cfg;
+    nprsph_constants consts;
+    nprsph_boundary bounds;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool paused = true;                 // `bool simulate;` starts false, Main.cpp:87
+    std::string err;
+    int sticky = 0;
+
+    struct { int nx, ny, nz; float spacing, origin[3], jitter; uint32_t seed; } scene;
+
+    uint64_t n = 0, cap = 0;
+    void* aos = nullptr;                // Particle[n], original order (SSBO binding 0)
+    float4* pos[2] = {nullptr, nullptr};
+    float4* vel[2] = {nullptr, nullptr};
+    float4* frc[2] = {nullptr, nullptr};
+    int cur = 0;
+    uint32_t* keys[2] = {nullptr, nullptr};
+    uint32_t* vals[2] = {nullptr, nullptr};
+    uint32_t* sorted_keys = nullptr;
+    uint32_t* last_perm = nullptr;
+    uint32_t* counts_rho = nullptr;
+    uint32_t* counts_force = nullptr;
+    void* sort_ws = nullptr;
+
+    uint32_t* cell_start = nullptr;
+    size_t cell_cap = 0;
+    uint4* gap_list = nullptr;
+    size_t gap_cap = 0;
+    uint32_t* gap_count = nullptr;      // also scratch for the NaN counter (8 bytes)
+
+    GridDev grid;
+    SphDev sph;
+    float cell_size = 0.f;
+    int key_bits = 1;
+    bool params_dirty = true;
+    bool keys_valid = false;
+    bool grid_valid = false;
+    bool aos_stale = false;             // SoA state is newer than the AoS view
+    uint64_t steps_done = 0;
+
+    cudaGraphicsResource* gl_res = nullptr;
+};
+
+namespace {
+
+int fail(nprsph_ctx* c, int code, const char* fmt, const char* detail = "") {
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, detail);
+    if (c) { c->err = buf; if (code == NPRSPH_ERR_CUDA) c->sticky = code; }
+    else g_create_error = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) return fail((ctx), NPRSPH_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+#define GUARD(ctx)                                                                        \
+    do {                                                                                  \
+        if (!(ctx)) return NPRSPH_ERR_INVALID;                                            \
+        if ((ctx)->sticky) return (ctx)->sticky;                                          \
+        cudaError_t e_ = cudaSetDevice((ctx)->cfg.device);                                \
+        if (e_ != cudaSuccess) return fail((ctx), NPRSPH_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+// Smallest fp32 t with sqrtf(t) >= h  (so `length(d) < h` == `r2 < t`; sqrtf is monotone).
+float r2_threshold(float h) {
+    if (!(h > 0.0f)) return 0.0f;
+    if (isinf(h)) return INFINITY;
+    float t = h * h;
+    while (t > 0.0f && sqrtf(nextafterf(t, 0.0f)) >= h) t = nextafterf(t, 0.0f);
+    while (sqrtf(t) < h) t = nextafterf(t, INFINITY);
+    return t;
+}
+
+// Uniform-grid definition (DESIGN.md "Grid"): cell = h*(1+2^-10)/subdiv, widened when an axis
+// would exceed 2048 cells or the table would exceed max_cells.
+int setup_grid(const nprsph_ctx* c, float h, GridDev* g, float* cell_size) {
+    int k = c->cfg.cell_subdiv;
+    if (!(h > 0.0f) || isinf(h) || k < 1 || k > 4) return -1;
+    double ext[3];
+    for (int a = 0; a < 3; a++) {
+        double e = (double)c->bounds.upper[a] - (double)c->bounds.lower[a];
+        if (!(e == e) || isinf(e)) return -2;
+        ext[a] = e > 0.0 ? e : 0.0;
+    }
+    uint32_t max_cells = c->cfg.max_cells ? c->cfg.max_cells : (1u << 28);
+    double cell = (double)h * (1.0 + 1.0 / 1024.0) / (double)k;
+    double dims[3] = {1, 1, 1};
+    for (int iter = 0; iter < 64; iter++) {
+        bool again = false;
+        for (int a = 0; a < 3; a++) {
+            dims[a] = floor(ext[a] / cell) + 1.0;
+            if (dims[a] > 2048.0) { cell = ext[a] / 2047.0; again = true; break; }
+        }
+        if (again) continue;
+        double total = dims[0] * dims[1] * dims[2];
+        if (total > (double)max_cells) { cell *= cbrt(total / (double)max_cells) * 1.0001; continue; }
+        break;
+    }
+    for (int a = 0; a < 3; a++) { g->lo[a] = c->bounds.lower[a]; g->dim[a] = (int)dims[a]; }
+    g->inv_cell = (float)(1.0 / cell);
+    g->reach = k;
+    g->num_cells = (uint32_t)((int64_t)g->dim[0] * g->dim[1] * g->dim[2]);
+    *cell_size = (float)cell;
+    return 0;
+}
+
+int refresh_params(nprsph_ctx* c) {
+    if (!c->params_dirty) return NPRSPH_OK;
+    const nprsph_config& cf = c->cfg;
+    SphDev s;
+    s.h = c->consts.smoothing_coeff * cf.particle_radius;       // rho_pres_comp.glsl:40
+    s.h2 = s.h * s.h;
+    s.r2_max = r2_threshold(s.h);
+    const double h = (double)s.h, pi = (double)cf.pi, m = (double)c->consts.mass;
+    s.rho_coef = (float)(m * 315.0 / (64.0 * pi * pow(h, 9.0)));            // :52
+    s.pres_coef = (float)(m * 45.0 / (2.0 * pi * pow(h, 6.0)));             // force_comp.glsl:41,59
+    s.visc_coef = (float)((double)c->consts.visc * m * 45.0 / (pi * pow(h, 6.0)));   // :42,60,63
+    s.gas_const = cf.gas_const;
+    s.rest_rho = c->consts.resting_rho;
+    for (int a = 0; a < 3; a++) {
+        s.g[a] = cf.gravity[a];
+        s.lower[a] = c->bounds.lower[a];
+        s.upper[a] = c->bounds.upper[a];
+    }
+    s.damping = cf.damping;
+    s.dt = cf.dt;
+
+    GridDev g;
+    float cell_size;
+    if (setup_grid(c, s.h, &g, &cell_size))
+        return fail(c, NPRSPH_ERR_INVALID, "cannot build a grid: smoothing length or bounds invalid%s");
+    if (memcmp(&g, &c->grid, sizeof g) != 0) { c->keys_valid = false; c->grid_valid = false; }
+    const size_t need = (size_t)g.num_cells + 2;
+    if (need > c->cell_cap) {
+        if (c->cell_start) CK(c, cudaFree(c->cell_start));
+        c->cell_start = nullptr; c->cell_cap = 0;
+        CK(c, cudaMalloc(&c->cell_start, need * sizeof(uint32_t)));
+        c->cell_cap = need;
+    }
+    const size_t gaps = gap_list_capacity(g.num_cells, c->cap ? c->cap : 1);
+    if (gaps > c->gap_cap) {
+        if (c->gap_list) CK(c, cudaFree(c->gap_list));
+        c->gap_list = nullptr; c->gap_cap = 0;
+        CK(c, cudaMalloc(&c->gap_list, gaps * sizeof(uint4)));
+        c->gap_cap = gaps;
+    }
+    c->grid = g;
+    c->sph = s;
+    c->cell_size = cell_size;
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) <= (uint64_t)g.num_cells) bits++;    // keys 0..num_cells
+    c->key_bits = bits;
+    c->params_dirty = false;
+    return NPRSPH_OK;
+}
+
+template <typename T>
+cudaError_t realloc_dev(T*& p, size_t count) {
+    if (p) { cudaError_t e = cudaFree(p); p = nullptr; if (e != cudaSuccess) return e; }
+    return count ? cudaMalloc(&p, count * sizeof(T)) : cudaSuccess;
+}
+
+int ensure_capacity(nprsph_ctx* c, uint64_t n) {
+    if (n >= (1ull << 30)) return fail(c, NPRSPH_ERR_INVALID, "at most 2^30-1 particles per context%s");
+    if (n <= c->cap) return NPRSPH_OK;
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->cap = 0;
+    { float4* a = (float4*)c->aos; CK(c, realloc_dev(a, n * 4)); c->aos = a; }
+    for (int b = 0; b < 2; b++) {
+        CK(c, realloc_dev(c->pos[b], n));
+        CK(c, realloc_dev(c->vel[b], n));
+        CK(c, realloc_dev(c->frc[b], n));
+        CK(c, realloc_dev(c->keys[b], n));
+        CK(c, realloc_dev(c->vals[b], n));
+    }
+    if (c->cfg.flags & NPRSPH_FLAG_COUNT_NEIGHBOURS) {
+        CK(c, realloc_dev(c->counts_rho, n));
+        CK(c, realloc_dev(c->counts_force, n));
+    }
+    { char* w = (char*)c->sort_ws; CK(c, realloc_dev(w, sort_workspace_bytes(n))); c->sort_ws = w; }
+    c->cap = n;
+    c->params_dirty = true;     // gap-list capacity depends on cap
+    return NPRSPH_OK;
+}
+
+// Bring the cell-ordered state and the cell table up to date with the current positions.
+int ensure_grid(nprsph_ctx* c, bool with_force, cudaEvent_t* ev /* 4 events or null */) {
+    int rc = refresh_params(c);
+    if (rc) return rc;
+    if (c->grid_valid || c->n == 0) {
+        if (ev) for (int i = 0; i < 4; i++) CK(c, cudaEventRecord(ev[i], c->stream));
+        return NPRSPH_OK;
+    }
+    const uint32_t n = (uint32_t)c->n;
+    if (ev) CK(c, cudaEventRecord(ev[0], c->stream));
+    if (!c->keys_valid) {
+        launch_keys(c->pos[c->cur], c->keys[0], n, c->grid, c->stream);
+        c->keys_valid = true;
+    }
+    if (ev) CK(c, cudaEventRecord(ev[1], c->stream));
+    bool in_b = false;
+    CK(c, sort_pairs(c->keys[0], c->vals[0], c->keys[1], c->vals[1], n, c->key_bits, true,
+                     c->sort_ws, c->num_sms, c->stream, &in_b));
+    c->sorted_keys = in_b ? c->keys[1] : c->keys[0];
+    c->last_perm = in_b ? c->vals[1] : c->vals[0];
+    if (ev) CK(c, cudaEventRecord(ev[2], c->stream));
+    const int nxt = 1 - c->cur;
+    launch_reorder_cells(c->sorted_keys, c->last_perm, c->pos[c->cur], c->vel[c->cur],
+                         c->frc[c->cur], c->pos[nxt], c->vel[nxt], c->frc[nxt], c->cell_start,
+                         c->grid.num_cells, n, c->gap_list, c->gap_count, with_force, c->num_sms,
+                         c->stream);
+    if (ev) CK(c, cudaEventRecord(ev[3], c->stream));
+    c->cur = nxt;
+    c->grid_valid = true;
+    CK(c, cudaGetLastError());
+    return NPRSPH_OK;
+}
+
+int run_rho(nprsph_ctx* c) {
+    launch_rho(c->pos[c->cur], c->vel[c->cur], c->cell_start, (uint32_t)c->n, c->grid, c->sph,
+               c->counts_rho, c->stream);
+    c->aos_stale = true;
+    return NPRSPH_OK;
+}
+
+int run_force(nprsph_ctx* c) {
+    launch_force(c->pos[c->cur], c->vel[c->cur], c->frc[c->cur], c->cell_start, (uint32_t)c->n,
+                 c->grid, c->sph, c->counts_force, c->stream);
+    c->aos_stale = true;
+    return NPRSPH_OK;
+}
+
+int run_integrate(nprsph_ctx* c) {
+    // keys for the next step are written where the sort expects its input
+    launch_integrate(c->pos[c->cur], c->vel[c->cur], c->frc[c->cur], c->keys[0], (uint32_t)c->n,
+                     c->grid, c->sph, c->stream);
+    c->keys_valid = true;
+    c->grid_valid = false;
+    c->sorted_keys = nullptr;
+    c->aos_stale = true;
+    return NPRSPH_OK;
+}
+
+int publish(nprsph_ctx* c) {
+    if (!c->aos_stale || c->n == 0) return NPRSPH_OK;
+    launch_publish(c->pos[c->cur], c->vel[c->cur], c->frc[c->cur], c->aos, (uint32_t)c->n, c->stream);
+    CK(c, cudaGetLastError());
+    c->aos_stale = false;
+    return NPRSPH_OK;
+}
+
+// after the AoS buffer was (re)written by upload or a scene kernel
+int adopt_aos(nprsph_ctx* c) {
+    c->cur = 0;
+    launch_import(c->aos, c->pos[0], c->vel[0], c->frc[0], (uint32_t)c->n, c->stream);
+    CK(c, cudaGetLastError());
+    c->keys_valid = false;
+    c->grid_valid = false;
+    c->aos_stale = false;
+    c->sorted_keys = nullptr;
+    return NPRSPH_OK;
+}
+
+__device__ __forceinline__ uint32_t hash32(uint32_t seed, uint32_t idx) {
+    uint32_t x = seed ^ (idx * 0x9E3779B9u);
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+
+// make_grid() + init_particles(), Main.cpp:488-521, generated on the device.
+__global__ void __launch_bounds__(256)
+k_scene_block(float4* __restrict__ aos, int nx, int ny, int nz, float spacing, float ox, float oy,
+              float oz, float jitter, uint32_t seed) {
+    const uint64_t n = (uint64_t)nx * ny * nz;
+    const uint64_t idx = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n) return;
+    const int k = (int)(idx % nz);
+    const int j = (int)((idx / nz) % ny);
+    const int i = (int)(idx / ((uint64_t)nz * ny));
+    float x = __fadd_rn(__fmul_rn((float)i, spacing), ox);
+    float y = __fadd_rn(__fmul_rn((float)j, spacing), oy);
+    float z = __fadd_rn(__fmul_rn((float)k, spacing), oz);
+    if (jitter > 0.0f) {
+        float c[3] = {x, y, z};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const uint32_t u = hash32(seed, (uint32_t)(3 * idx + a));
+            const float f = __fmul_rn((float)(u >> 8), 1.0f / 16777216.0f);
+            c[a] = __fadd_rn(c[a], __fmul_rn(__fsub_rn(__fmul_rn(2.0f, f), 1.0f), jitter));
+        }
+        x = c[0]; y = c[1]; z = c[2];
+    }
+    aos[4 * idx + 0] = make_float4(x, y, z, 1.0f);
+    aos[4 * idx + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    aos[4 * idx + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    aos[4 * idx + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+int build_scene(nprsph_ctx* c) {
+    const uint64_t n = (uint64_t)c->scene.nx * c->scene.ny * c->scene.nz;
+    int rc = ensure_capacity(c, n);
+    if (rc) return rc;
+    c->n = n;
+    if (n) {
+        k_scene_block<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+            (float4*)c->aos, c->scene.nx, c->scene.ny, c->scene.nz, c->scene.spacing,
+            c->scene.origin[0], c->scene.origin[1], c->scene.origin[2], c->scene.jitter, c->scene.seed);
+        CK(c, cudaGetLastError());
+    }
+    return adopt_aos(c);
+}
+
+bool config_ok(const nprsph_config* cfg) {
+    return cfg && cfg->struct_size == sizeof(nprsph_config) && cfg->cell_subdiv >= 0 && cfg->cell_subdiv <= 4;
+}
+
+}  // namespace
+
+// ================================ C ABI ==========================================================
+extern "C" {
+
+int nprsph_abi_version(void) { return NPRSPH_ABI_VERSION; }
+
+void nprsph_config_default(nprsph_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = sizeof *cfg;
+    cfg->device = 0;
+    cfg->stream = nullptr;
+    cfg->particle_radius = 0.005f;
+    cfg->gas_const = 2000.0f;
+    cfg->gravity[0] = 0.0f; cfg->gravity[1] = -9806.65f; cfg->gravity[2] = 0.0f;
+    cfg->damping = 0.3f;
+    cfg->dt = 1.0f / 10000.0f;
+    cfg->pi = 3.141592741f;
+    cfg->cell_subdiv = 1;
+    cfg->max_cells = 0;
+    cfg->flags = 0;
+}
+
+const char* nprsph_last_error(const nprsph_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int nprsph_create(const nprsph_config* cfg, nprsph_ctx** out) {
+    if (!out) return NPRSPH_ERR_INVALID;
+    *out = nullptr;
+    if (!config_ok(cfg)) return fail(nullptr, NPRSPH_ERR_INVALID, "bad nprsph_config (struct_size / cell_subdiv)%s");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, NPRSPH_ERR_CUDA, "no CUDA device: %s (libnprsph has no CPU path)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (cfg->device < 0 || cfg->device >= count) return fail(nullptr, NPRSPH_ERR_INVALID, "bad device ordinal%s");
+    CK(nullptr, cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(nullptr, NPRSPH_ERR_UNSUPPORTED, "libnprsph is built for sm_100a only; device is %s", prop.name);
+    nprsph_ctx* c = new (std::nothrow) nprsph_ctx();
+    if (!c) return fail(nullptr, NPRSPH_ERR_NOMEM, "out of host memory%s");
+    c->cfg = *cfg;
+    if (c->cfg.cell_subdiv == 0) c->cfg.cell_subdiv = 1;
+    c->num_sms = prop.multiProcessorCount;
+    // ConstantsData / BoundaryData defaults, Main.cpp:110-122
+    c->consts = {0.02f, 4.0f, 3000.0f, 1000.0f};
+    c->bounds = {{0.5f, 1.0f, 0.5f, 1.0f}, {-0.1f, -0.35f, -0.1f, 1.0f}};
+    // make_grid(): 10 x 100 x 10 at PARTICLE_RADIUS spacing, Main.cpp:488-505
+    c->scene = {10, 100, 10, cfg->particle_radius, {0.f, 0.f, 0.f}, 0.f, 0u};
+    memset(&c->grid, 0, sizeof c->grid);
+    memset(&c->sph, 0, sizeof c->sph);
+    if (cfg->stream) { c->stream = (cudaStream_t)cfg->stream; c->own_stream = false; }
+    else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail(nullptr, NPRSPH_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        c->own_stream = true;
+    }
+    e = cudaMalloc(&c->gap_count, 16);
+    if (e != cudaSuccess) { nprsph_destroy(c); return fail(nullptr, NPRSPH_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    int rc = build_scene(c);      // initOpenGL() -> init_particles(), Main.cpp:567
+    if (rc) { g_create_error = c->err; nprsph_destroy(c); return rc; }
+    *out = c;
+    return NPRSPH_OK;
+}
+
+int nprsph_destroy(nprsph_ctx* c) {
+    if (!c) return NPRSPH_OK;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->gl_res) cudaGraphicsUnregisterResource(c->gl_res);
+    cudaFree(c->aos);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(c->pos[b]); cudaFree(c->vel[b]); cudaFree(c->frc[b]);
+        cudaFree(c->keys[b]); cudaFree(c->vals[b]);
+    }
+    cudaFree(c->counts_rho); cudaFree(c->counts_force); cudaFree(c->sort_ws);
+    cudaFree(c->cell_start); cudaFree(c->gap_list); cudaFree(c->gap_count);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return NPRSPH_OK;
+}
+
+// ---- parameters ------------------------------------------------------------------------------------
+int nprsph_set_constants(nprsph_ctx* c, const nprsph_constants* k) {
+    if (!c || !k) return NPRSPH_ERR_INVALID;
+    c->consts = *k;
+    c->params_dirty = true;
+    return NPRSPH_OK;
+}
+int nprsph_get_constants(const nprsph_ctx* c, nprsph_constants* k) {
+    if (!c || !k) return NPRSPH_ERR_INVALID;
+    *k = c->consts;
+    return NPRSPH_OK;
+}
+int nprsph_set_boundary(nprsph_ctx* c, const nprsph_boundary* b) {
+    if (!c || !b) return NPRSPH_ERR_INVALID;
+    c->bounds = *b;
+    c->params_dirty = true;
+    return NPRSPH_OK;
+}
+int nprsph_get_boundary(const nprsph_ctx* c, nprsph_boundary* b) {
+    if (!c || !b) return NPRSPH_ERR_INVALID;
+    *b = c->bounds;
+    return NPRSPH_OK;
+}
+int nprsph_set_config(nprsph_ctx* c, const nprsph_config* cfg) {
+    if (!c) return NPRSPH_ERR_INVALID;
+    if (!config_ok(cfg)) return fail(c, NPRSPH_ERR_INVALID, "bad nprsph_config%s");
+    if (cfg->device != c->cfg.device || cfg->stream != c->cfg.stream)
+        return fail(c, NPRSPH_ERR_INVALID, "device and stream are fixed at create time%s");
+    if ((cfg->flags ^ c->cfg.flags) & NPRSPH_FLAG_COUNT_NEIGHBOURS)
+        return fail(c, NPRSPH_ERR_INVALID, "NPRSPH_FLAG_COUNT_NEIGHBOURS is fixed at create time%s");
+    c->cfg = *cfg;
+    if (c->cfg.cell_subdiv == 0) c->cfg.cell_subdiv = 1;
+    c->params_dirty = true;
+    return NPRSPH_OK;
+}
+int nprsph_get_config(const nprsph_ctx* c, nprsph_config* cfg) {
+    if (!c || !cfg) return NPRSPH_ERR_INVALID;
+    *cfg = c->cfg;
+    return NPRSPH_OK;
+}
+
+// ---- particle buffer -------------------------------------------------------------------------------
+int nprsph_scene_block(nprsph_ctx* c, int nx, int ny, int nz, float spacing, const float origin[3],
+                       float jitter, uint32_t seed) {
+    GUARD(c);
+    if (nx < 0 || ny < 0 || nz < 0) return fail(c, NPRSPH_ERR_INVALID, "negative block size%s");
+    c->scene.nx = nx; c->scene.ny = ny; c->scene.nz = nz;
+    c->scene.spacing = spacing;
+    for (int a = 0; a < 3; a++) c->scene.origin[a] = origin ? origin[a] : 0.0f;
+    c->scene.jitter = jitter;
+    c->scene.seed = seed;
+    return build_scene(c);
+}
+
+int nprsph_upload_particles(nprsph_ctx* c, const nprsph_particle* host, uint64_t n) {
+    GUARD(c);
+    if (n && !host) return fail(c, NPRSPH_ERR_INVALID, "null host buffer%s");
+    int rc = ensure_capacity(c, n);
+    if (rc) return rc;
+    c->n = n;
+    if (n) CK(c, cudaMemcpyAsync(c->aos, host, n * sizeof(nprsph_particle), cudaMemcpyHostToDevice, c->stream));
+    return adopt_aos(c);
+}
+
+int nprsph_download_particles(nprsph_ctx* c, nprsph_particle* host, uint64_t n) {
+    GUARD(c);
+    if (n > c->n) return fail(c, NPRSPH_ERR_INVALID, "download larger than the particle buffer%s");
+    if (n && !host) return fail(c, NPRSPH_ERR_INVALID, "null host buffer%s");
+    int rc = publish(c);
+    if (rc) return rc;
+    if (n) CK(c, cudaMemcpyAsync(host, c->aos, n * sizeof(nprsph_particle), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return NPRSPH_OK;
+}
+
+int nprsph_device_particles(nprsph_ctx* c, void** device_ptr, uint64_t* n) {
+    GUARD(c);
+    if (!device_ptr) return NPRSPH_ERR_INVALID;
+    int rc = publish(c);
+    if (rc) return rc;
+    *device_ptr = c->aos;
+    if (n) *n = c->n;
+    return NPRSPH_OK;
+}
+
+uint64_t nprsph_num_particles(const nprsph_ctx* c) { return c ? c->n : 0; }
+
+// ---- pause / reset ---------------------------------------------------------------------------------
+int nprsph_set_paused(nprsph_ctx* c, int paused) {
+    if (!c) return NPRSPH_ERR_INVALID;
+    c->paused = paused != 0;
+    return NPRSPH_OK;
+}
+int nprsph_toggle_pause(nprsph_ctx* c) {           // 'p', Main.cpp:466-469
+    if (!c) return NPRSPH_ERR_INVALID;
+    c->paused = !c->paused;
+    return NPRSPH_OK;
+}
+int nprsph_is_paused(const nprsph_ctx* c) { return c ? (c->paused ? 1 : 0) : NPRSPH_ERR_INVALID; }
+
+int nprsph_reset(nprsph_ctx* c) {                  // 'r', Main.cpp:460-464
+    GUARD(c);
+    return build_scene(c);                         // pause flag and constants untouched
+}
+
+// ---- stepping ----------------------------------------------------------------------------------------
+static int step_once(nprsph_ctx* c) {
+    int rc = ensure_grid(c, false, nullptr);
+    if (rc) return rc;
+    run_rho(c);                                    // Main.cpp:295-297
+    run_force(c);                                  // Main.cpp:298-300
+    run_integrate(c);                              // Main.cpp:301-303
+    c->steps_done++;
+    return NPRSPH_OK;
+}
+
+int nprsph_step(nprsph_ctx* c, int n_steps) {
+    GUARD(c);
+    if (n_steps < 0) return fail(c, NPRSPH_ERR_INVALID, "negative step count%s");
+    if (c->paused || c->n == 0) return NPRSPH_OK;  // if (simulate) ..., Main.cpp:293
+    for (int s = 0; s < n_steps; s++) {
+        int rc = step_once(c);
+        if (rc) return rc;
+    }
+    CK(c, cudaGetLastError());
+    return NPRSPH_OK;
+}
+
+int nprsph_sync(nprsph_ctx* c) {
+    GUARD(c);
+    CK(c, cudaStreamSynchronize(c->stream));
+    return NPRSPH_OK;
+}
+
+int nprsph_pass_rho(nprsph_ctx* c) {
+    GUARD(c);
+    if (c->n == 0) return NPRSPH_OK;
+    int rc = ensure_grid(c, true, nullptr);
+    if (rc) return rc;
+    run_rho(c);
+    CK(c, cudaGetLastError());
+    return NPRSPH_OK;
+}
+
+int nprsph_pass_force(nprsph_ctx* c) {
+    GUARD(c);
+    if (c->n == 0) return NPRSPH_OK;
+    int rc = ensure_grid(c, true, nullptr);
+    if (rc) return rc;
+    run_force(c);
+    CK(c, cudaGetLastError());
+    return NPRSPH_OK;
+}
+
+int nprsph_pass_integrate(nprsph_ctx* c) {
+    GUARD(c);
+    if (c->n == 0) return NPRSPH_OK;
+    int rc = refresh_params(c);
+    if (rc) return rc;
+    run_integrate(c);
+    CK(c, cudaGetLastError());
+    return NPRSPH_OK;
+}
+
+void* nprsph_stream(const nprsph_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---- measurement / introspection ---------------------------------------------------------------------
+int nprsph_get_stats(nprsph_ctx* c, nprsph_stats* out) {
+    GUARD(c);
+    if (!out) return NPRSPH_ERR_INVALID;
+    int rc = refresh_params(c);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->num_particles = c->n;
+    out->steps_done = c->steps_done;
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(c->gap_count) + 1;
+    launch_count_nan(c->pos[c->cur], (uint32_t)c->n, d_cnt, c->stream);
+    unsigned long long h_cnt = 0;
+    CK(c, cudaMemcpyAsync(&h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    out->nan_particles = h_cnt;
+    out->num_cells = c->grid.num_cells;
+    for (int a = 0; a < 3; a++) out->grid_dim[a] = (uint32_t)c->grid.dim[a];
+    out->key_bits = (uint32_t)c->key_bits;
+    out->sort_passes = (uint32_t)sort_num_passes(c->key_bits);
+    out->cell_size = c->cell_size;
+    out->smoothing_length = c->sph.h;
+    out->paused = c->paused ? 1 : 0;
+    out->cell_subdiv = c->cfg.cell_subdiv;
+    return NPRSPH_OK;
+}
+
+int nprsph_profile_step(nprsph_ctx* c, int n_steps, float* stage_ms) {
+    GUARD(c);
+    if (n_steps < 1 || !stage_ms) return NPRSPH_ERR_INVALID;
+    cudaEvent_t ev[8];
+    for (int i = 0; i < 8; i++) CK(c, cudaEventCreate(&ev[i]));
+    double acc[NPRSPH_NUM_STAGES] = {0};
+    int rc = NPRSPH_OK;
+    for (int s = 0; s < n_steps && rc == NPRSPH_OK && c->n; s++) {
+        rc = ensure_grid(c, false, ev);            // ev[0..3]
+        if (rc) break;
+        CK(c, cudaEventRecord(ev[4], c->stream));
+        run_rho(c);
+        CK(c, cudaEventRecord(ev[5], c->stream));
+        run_force(c);
+        CK(c, cudaEventRecord(ev[6], c->stream));
+        run_integrate(c);
+        CK(c, cudaEventRecord(ev[7], c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        c->steps_done++;
+        const int stage_of[7] = {NPRSPH_STAGE_KEYS, NPRSPH_STAGE_SORT, NPRSPH_STAGE_REORDER, -1,
+                                 NPRSPH_STAGE_RHO, NPRSPH_STAGE_FORCE, NPRSPH_STAGE_INTEGRATE};
+        for (int i = 0; i < 7; i++) {
+            if (stage_of[i] < 0) continue;
+            float ms = 0.f;
+            CK(c, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            acc[stage_of[i]] += ms;
+        }
+    }
+    for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]);
+    // cell table construction is fused into the reorder kernel; it is reported with REORDER
+    for (int i = 0; i < NPRSPH_NUM_STAGES; i++) stage_ms[i] = (float)(acc[i] / n_steps);
+    return rc;
+}
+
+int nprsph_debug_read(nprsph_ctx* c, int item, void* dst, uint64_t bytes) {
+    GUARD(c);
+    if (!dst) return NPRSPH_ERR_INVALID;
+    const void* src = nullptr;
+    uint64_t need = 0;
+    uint32_t* tmp = nullptr;
+    switch (item) {
+        case NPRSPH_DBG_SORTED_KEYS:
+        case NPRSPH_DBG_CELL_START:
+        case NPRSPH_DBG_LAST_PERM:
+        case NPRSPH_DBG_SLOT_IDS: {
+            int rc = ensure_grid(c, true, nullptr);
+            if (rc) return rc;
+            if (item == NPRSPH_DBG_CELL_START) { src = c->cell_start; need = ((uint64_t)c->grid.num_cells + 2) * 4; }
+            else if (item == NPRSPH_DBG_SORTED_KEYS) { src = c->sorted_keys; need = c->n * 4; }
+            else if (item == NPRSPH_DBG_LAST_PERM) { src = c->last_perm; need = c->n * 4; }
+            else {
+                CK(c, cudaMalloc(&tmp, (c->n ? c->n : 1) * 4));
+                launch_slot_ids(c->pos[c->cur], tmp, (uint32_t)c->n, c->stream);
+                src = tmp; need = c->n * 4;
+            }
+            break;
+        }
+        case NPRSPH_DBG_COUNTS_RHO: src = c->counts_rho; need = c->n * 4; break;
+        case NPRSPH_DBG_COUNTS_FORCE: src = c->counts_force; need = c->n * 4; break;
+        default: return fail(c, NPRSPH_ERR_INVALID, "unknown debug item%s");
+    }
+    int rc = NPRSPH_OK;
+    if (need && !src) rc = fail(c, NPRSPH_ERR_STATE, "debug item not available (flag not set or no grid yet)%s");
+    else if (bytes != need) rc = fail(c, NPRSPH_ERR_INVALID, "debug_read: wrong byte count%s");
+    else if (need) {
+        cudaError_t e = cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(c, NPRSPH_ERR_CUDA, "debug_read copy: %s", cudaGetErrorString(e));
+    }
+    if (tmp) { cudaStreamSynchronize(c->stream); cudaFree(tmp); }
+    return rc;
+}
+
+int nprsph_sort_pairs_host(int device, const uint32_t* keys_in, const uint32_t* vals_in, uint64_t n,
+                           int key_bits, uint32_t* keys_out, uint32_t* vals_out) {
+    if ((n && (!keys_in || !keys_out || !vals_out)) || key_bits < 1 || key_bits > 32) return NPRSPH_ERR_INVALID;
+    if (n == 0) return NPRSPH_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return NPRSPH_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NPRSPH_ERR_CUDA;
+    uint32_t *k[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr};
+    void* ws = nullptr;
+    int rc = NPRSPH_OK;
+    cudaStream_t st = nullptr;
+    bool in_b = false;
+    cudaError_t e = cudaSuccess;
+#define SK(call) do { e = (call); if (e != cudaSuccess) { rc = NPRSPH_ERR_CUDA; goto done; } } while (0)
+    SK(cudaStreamCreate(&st));
+    for (int b = 0; b < 2; b++) { SK(cudaMalloc(&k[b], n * 4)); SK(cudaMalloc(&v[b], n * 4)); }
+    SK(cudaMalloc(&ws, sort_workspace_bytes(n)));
+    SK(cudaMemcpyAsync(k[0], keys_in, n * 4, cudaMemcpyHostToDevice, st));
+    if (vals_in) SK(cudaMemcpyAsync(v[0], vals_in, n * 4, cudaMemcpyHostToDevice, st));
+    SK(sort_pairs(k[0], v[0], k[1], v[1], n, key_bits, vals_in == nullptr, ws, prop.multiProcessorCount, st, &in_b));
+    SK(cudaMemcpyAsync(keys_out, in_b ? k[1] : k[0], n * 4, cudaMemcpyDeviceToHost, st));
+    SK(cudaMemcpyAsync(vals_out, in_b ? v[1] : v[0], n * 4, cudaMemcpyDeviceToHost, st));
+    SK(cudaStreamSynchronize(st));
+#undef SK
+done:
+    if (e != cudaSuccess) g_create_error = cudaGetErrorString(e);
+    for (int b = 0; b < 2; b++) { cudaFree(k[b]); cudaFree(v[b]); }
+    cudaFree(ws);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+// ---- OpenGL presenter ---------------------------------------------------------------------------------
+int nprsph_gl_register(nprsph_ctx* c, unsigned int gl_buffer) {
+    GUARD(c);
+    if (c->gl_res) return fail(c, NPRSPH_ERR_STATE, "a GL buffer is already registered%s");
+    cudaError_t e = cudaGraphicsGLRegisterBuffer(&c->gl_res, gl_buffer, 0 /* cudaGraphicsRegisterFlagsNone */);
+    if (e != cudaSuccess) {
+        c->gl_res = nullptr;
+        cudaGetLastError();      // not sticky: the caller simply has no usable GL context
+        return fail(c, NPRSPH_ERR_UNSUPPORTED, "cudaGraphicsGLRegisterBuffer: %s", cudaGetErrorString(e));
+    }
+    return NPRSPH_OK;
+}
+
+int nprsph_gl_publish(nprsph_ctx* c) {
+    GUARD(c);
+    if (!c->gl_res) return fail(c, NPRSPH_ERR_STATE, "no GL buffer registered%s");
+    int rc = publish(c);
+    if (rc) return rc;
+    CK(c, cudaGraphicsMapResources(1, &c->gl_res, c->stream));
+    void* p = nullptr; size_t sz = 0;
+    cudaError_t e = cudaGraphicsResourceGetMappedPointer(&p, &sz, c->gl_res);
+    if (e == cudaSuccess && sz < c->n * sizeof(nprsph_particle)) e = cudaErrorInvalidValue;
+    if (e == cudaSuccess && c->n)
+        e = cudaMemcpyAsync(p, c->aos, c->n * sizeof(nprsph_particle), cudaMemcpyDeviceToDevice, c->stream);
+    cudaGraphicsUnmapResources(1, &c->gl_res, c->stream);
+    if (e != cudaSuccess) return fail(c, NPRSPH_ERR_CUDA, "gl_publish: %s", cudaGetErrorString(e));
+    return NPRSPH_OK;
+}
+
+int nprsph_gl_unregister(nprsph_ctx* c) {
+    GUARD(c);
+    if (!c->gl_res) return NPRSPH_OK;
+    CK(c, cudaGraphicsUnregisterResource(c->gl_res));
+    c->gl_res = nullptr;
+    return NPRSPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// common.cuh -- device-side parameter blocks and helpers shared by all kernels.
+// sm_100a only; there is deliberately no host/CPU implementation of any pass.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nprsph {
+
+// Uniform-grid definition (DESIGN.md "Grid").  The same arithmetic is restated in
+// oracle/sph_oracle.c:oracle_grid_setup / cell_key so keys can be compared bit-exactly.
+struct GridDev {
+    float lo[3];
+    float inv_cell;
+    int   dim[3];
+    int   reach;          // cells walked on each side of the home cell
+    uint32_t num_cells;   // sentinel key (NaN positions) == num_cells
+};
+
+// Run-time constants of the three passes.  Sources: ConstantsUniform / BoundaryUniform
+// (Main.cpp:110-122) and the shader consts (rho_pres_comp.glsl:5,8,33; force_comp.glsl:33;
+// integrate_comp.glsl:8,33).
+struct SphDev {
+    float h;            // smoothing_coeff * particle_radius   (rho_pres_comp.glsl:40)
+    float h2;           // h*h
+    float r2_max;       // smallest t with sqrt_rn(t) >= h  =>  (length(d) < h) == (r2 < r2_max)
+    float rho_coef;     // mass*315 / (64*pi*h^9)             (rho_pres_comp.glsl:52)
+    float pres_coef;    // -mass*spiky/2 = mass*45/(2*pi*h^6) (force_comp.glsl:41,59)
+    float visc_coef;    // visc*mass*laplacian                (force_comp.glsl:42,60,63)
+    float gas_const;
+    float rest_rho;
+    float g[3];
+    float damping;
+    float dt;
+    float lower[3];
+    float upper[3];
+};
+
+__device__ __forceinline__ int cell_coord(float x, float lo, float inv_cell, int dim) {
+    // (x - lo) * inv_cell with two individually rounded operations (no FMA contraction)
+    float u = __fmul_rn(__fsub_rn(x, lo), inv_cell);
+    if (!(u >= 0.0f)) u = 0.0f;
+    const float top = (float)(dim - 1);
+    if (u > top) u = top;
+    return (int)u;
+}
+
+__device__ __forceinline__ bool pos_is_nan(float x, float y, float z) {
+    return (x != x) || (y != y) || (z != z);
+}
+
+__device__ __forceinline__ uint32_t cell_key(float x, float y, float z, const GridDev& g) {
+    if (pos_is_nan(x, y, z)) return g.num_cells;
+    const int cx = cell_coord(x, g.lo[0], g.inv_cell, g.dim[0]);
+    const int cy = cell_coord(y, g.lo[1], g.inv_cell, g.dim[1]);
+    const int cz = cell_coord(z, g.lo[2], g.inv_cell, g.dim[2]);
+    return ((uint32_t)cx * (uint32_t)g.dim[1] + (uint32_t)cy) * (uint32_t)g.dim[2] + (uint32_t)cz;
+}
+
+// The neighbour predicate of the shaders, `length(pos_i - pos_j) < h`
+// (rho_pres_comp.glsl:48-50, force_comp.glsl:55-57), evaluated as r2 < r2_max with r2 built
+// from individually rounded operations in the oracle's order: (dx*dx + dy*dy) + dz*dz.
+__device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// GLSL max(a,b) = (a < b) ? b : a
+__device__ __forceinline__ float glsl_max(float a, float b) { return (a < b) ? b : a; }
+
+__device__ __forceinline__ float eos_pressure(float rho, const SphDev& s) {
+    // max(GAS_CONST * (rho - resting_rho), 0)   rho_pres_comp.glsl:58
+    return glsl_max(__fmul_rn(s.gas_const, __fsub_rn(rho, s.rest_rho)), 0.0f);
+}
+
+
+}  // namespace nprsph

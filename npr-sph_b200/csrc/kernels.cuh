@@ -1,0 +1,31 @@
+// kernels.cuh -- launchers of every device kernel (implemented in grid.cu / sph_passes.cu).
+#pragma once
+#include "common.cuh"
+
+namespace nprsph {
+
+// grid.cu
+void launch_import(const void* aos, float4* posid, float4* velrho, float4* forcep, uint32_t n,
+                   cudaStream_t st);
+void launch_publish(const float4* posid, const float4* velrho, const float4* forcep, void* aos,
+                    uint32_t n, cudaStream_t st);
+void launch_keys(const float4* posid, uint32_t* keys, uint32_t n, const GridDev& g, cudaStream_t st);
+size_t gap_list_capacity(uint32_t num_cells, uint64_t n);
+void launch_reorder_cells(const uint32_t* sorted_keys, const uint32_t* perm, const float4* pos_in,
+                          const float4* vel_in, const float4* force_in, float4* pos_out,
+                          float4* vel_out, float4* force_out, uint32_t* cell_start,
+                          uint32_t num_cells, uint32_t n, uint4* gap_list, uint32_t* gap_count,
+                          bool with_force, int num_sms, cudaStream_t st);
+void launch_count_nan(const float4* posid, uint32_t n, unsigned long long* out, cudaStream_t st);
+void launch_slot_ids(const float4* posid, uint32_t* ids, uint32_t n, cudaStream_t st);
+
+// sph_passes.cu
+void launch_rho(const float4* posid, float4* velrho, const uint32_t* cell_start, uint32_t n,
+                const GridDev& g, const SphDev& sp, uint32_t* counts_by_id, cudaStream_t st);
+void launch_force(const float4* posid, const float4* velrho, float4* forcep,
+                  const uint32_t* cell_start, uint32_t n, const GridDev& g, const SphDev& sp,
+                  uint32_t* counts_by_id, cudaStream_t st);
+void launch_integrate(float4* posid, float4* velrho, const float4* forcep, uint32_t* keys,
+                      uint32_t n, const GridDev& g, const SphDev& sp, cudaStream_t st);
+
+}  // namespace nprsph

@@ -193,3 +193,30 @@ def cell_keys(P, g) -> np.ndarray:
 
 def num_threads() -> int:
     return lib().oracle_num_threads()
+
+
+# ---- GPU all-pairs oracle (tests only; needs a CUDA device) ------------------------------------
+_GPU_LIB_PATH = os.path.join(_HERE, "_build", "liballpairs_gpu.so")
+_gpu = None
+
+
+def gpu_lib():
+    global _gpu
+    if _gpu is None:
+        if not os.path.exists(_GPU_LIB_PATH):
+            subprocess.check_call(["make", "-C", _HERE, "_build/liballpairs_gpu.so"],
+                                  stdout=subprocess.DEVNULL)
+        L = C.CDLL(_GPU_LIB_PATH)
+        L.oracle_gpu_pass.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(Params),
+                                      C.POINTER(C.c_uint32)]
+        L.oracle_gpu_pass.restype = C.c_int
+        _gpu = L
+    return _gpu
+
+
+def gpu_pass(which: int, P, p, counts=False):
+    """which: 0 = rho/pressure pass, 1 = force pass; brute force over all pairs on the GPU."""
+    c = np.zeros(len(P), np.uint32) if counts else None
+    rc = gpu_lib().oracle_gpu_pass(which, _fp(P), len(P), C.byref(p), _u32(c))
+    assert rc == 0, "GPU all-pairs oracle failed"
+    return c
