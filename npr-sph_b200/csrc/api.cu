@@ -252,9 +252,9 @@ int ensure_grid(nprsph_ctx* c, bool with_force, cudaEvent_t* ev /* 4 events or n
     return NPRSPH_OK;
 }
 
-int run_rho(nprsph_ctx* c) {
-    launch_rho(c->pos[c->cur], c->vel[c->cur], c->cell_start, (uint32_t)c->n, c->grid, c->sph,
-               c->counts_rho, c->stream);
+int run_rho(nprsph_ctx* c, bool write_pressure) {
+    launch_rho(c->pos[c->cur], c->vel[c->cur], write_pressure ? c->frc[c->cur] : nullptr,
+               c->cell_start, (uint32_t)c->n, c->grid, c->sph, c->counts_rho, c->stream);
     c->aos_stale = true;
     return NPRSPH_OK;
 }
@@ -545,7 +545,7 @@ int nprsph_reset(nprsph_ctx* c) {                  // 'r', Main.cpp:460-464
 static int step_once(nprsph_ctx* c) {
     int rc = ensure_grid(c, false, nullptr);
     if (rc) return rc;
-    run_rho(c);                                    // Main.cpp:295-297
+    run_rho(c, false);                             // Main.cpp:295-297
     run_force(c);                                  // Main.cpp:298-300
     run_integrate(c);                              // Main.cpp:301-303
     c->steps_done++;
@@ -575,7 +575,7 @@ int nprsph_pass_rho(nprsph_ctx* c) {
     if (c->n == 0) return NPRSPH_OK;
     int rc = ensure_grid(c, true, nullptr);
     if (rc) return rc;
-    run_rho(c);
+    run_rho(c, true);
     CK(c, cudaGetLastError());
     return NPRSPH_OK;
 }
@@ -639,7 +639,7 @@ int nprsph_profile_step(nprsph_ctx* c, int n_steps, float* stage_ms) {
         rc = ensure_grid(c, false, ev);            // ev[0..3]
         if (rc) break;
         CK(c, cudaEventRecord(ev[4], c->stream));
-        run_rho(c);
+        run_rho(c, false);
         CK(c, cudaEventRecord(ev[5], c->stream));
         run_force(c);
         CK(c, cudaEventRecord(ev[6], c->stream));

@@ -20,8 +20,9 @@ void launch_count_nan(const float4* posid, uint32_t n, unsigned long long* out, 
 void launch_slot_ids(const float4* posid, uint32_t* ids, uint32_t n, cudaStream_t st);
 
 // sph_passes.cu
-void launch_rho(const float4* posid, float4* velrho, const uint32_t* cell_start, uint32_t n,
-                const GridDev& g, const SphDev& sp, uint32_t* counts_by_id, cudaStream_t st);
+void launch_rho(const float4* posid, float4* velrho, float4* forcep_or_null,
+                const uint32_t* cell_start, uint32_t n, const GridDev& g, const SphDev& sp,
+                uint32_t* counts_by_id, cudaStream_t st);
 void launch_force(const float4* posid, const float4* velrho, float4* forcep,
                   const uint32_t* cell_start, uint32_t n, const GridDev& g, const SphDev& sp,
                   uint32_t* counts_by_id, cudaStream_t st);

@@ -69,6 +69,7 @@ def lib():
         L.oracle_pass_force.argtypes = [fp, C.c_int, pp, u32p]
         L.oracle_pass_integrate.argtypes = [fp, C.c_int, pp]
         L.oracle_step.argtypes = [fp, C.c_int, pp, C.c_int]
+        L.oracle_force_scale.argtypes = [fp, C.c_int, pp, fp]
         L.oracle_sample_update.argtypes = [fp, C.c_int, pp, i32p, C.c_int, fp]
         L.oracle_grid_setup.argtypes = [pp, C.c_int, C.c_uint32, gp]
         L.oracle_grid_setup.restype = C.c_int
@@ -155,6 +156,13 @@ def pass_force(P, p, counts=False, grid=0):
     else:
         lib().oracle_pass_force(_fp(P), len(P), C.byref(p), _u32(c))
     return c
+
+
+def force_scale(P, p) -> np.ndarray:
+    """Sum of |terms| of the force sums, shape (n, 3); P must hold rho/p (after pass_rho)."""
+    out = np.empty((len(P), 3), np.float32)
+    lib().oracle_force_scale(_fp(P), len(P), C.byref(p), _fp(out))
+    return out
 
 
 def pass_integrate(P, p):

@@ -200,6 +200,32 @@ void oracle_pass_force(float* P, int n, const oracle_params* p, uint32_t* counts
     free(f_out);
 }
 
+/* Condition scale of the force sums: per particle and component, the sum of the absolute
+ * values of everything force_comp.glsl adds up (|pressure terms| + visc*|viscosity terms| +
+ * |rho*G|).  Any fp32 evaluation that re-orders or re-associates the sum can differ from
+ * another by about eps * sqrt(terms) * this scale, however small the net force is, so parity
+ * tests bound the element-wise error against it. */
+void oracle_force_scale(const float* P, int n, const oracle_params* p, float* scale3) {
+    const float h = oracle_smoothing_length(p);
+    const float h6 = pow_once(h, 6);
+    const float spiky = -45.0f / (p->pi * h6);
+    const float lap = 45.0f / (p->pi * h6);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        const float* pi_ = P + (size_t)i * ORACLE_REC;
+        double acc[3] = {0, 0, 0};
+        for (int j = 0; j < n; j++) {
+            if (i == j) continue;
+            force_acc a; memset(&a, 0, sizeof a);
+            if (force_term(pi_, P + (size_t)j * ORACLE_REC, h, p->mass, spiky, lap, &a))
+                for (int k = 0; k < 3; k++)
+                    acc[k] += fabs((double)a.pres[k]) + fabs((double)a.visc[k] * p->visc);
+        }
+        for (int k = 0; k < 3; k++)
+            scale3[3 * (size_t)i + k] = (float)(acc[k] + fabs((double)pi_[12] * p->gravity[k]));
+    }
+}
+
 /* ---- integrate_comp.glsl:35-82 ---------------------------------------------------- */
 static void integrate_one(float* r, const oracle_params* p) {
     for (int k = 0; k < 3; k++) {

@@ -64,6 +64,8 @@ float oracle_r2_threshold(float h);
 void oracle_pass_rho(float* particles, int n, const oracle_params* p, uint32_t* counts);
 void oracle_pass_force(float* particles, int n, const oracle_params* p, uint32_t* counts);
 void oracle_pass_integrate(float* particles, int n, const oracle_params* p);
+/* sum of |terms| of the force sums per particle/component (conditioning scale for tests) */
+void oracle_force_scale(const float* particles, int n, const oracle_params* p, float* scale3);
 void oracle_step(float* particles, int n, const oracle_params* p, int n_steps);
 
 /* all-pairs, but only for the m particles listed in idx (bounded CPU baseline) */

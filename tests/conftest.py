@@ -34,14 +34,18 @@ def pytest_collection_modifyitems(config, items):
 REL_TOL = 1e-5
 
 
-def assert_field_close(got, want, name, tol=REL_TOL):
+def assert_field_close(got, want, name, tol=REL_TOL, scale=None, elementwise=True):
     """NaN-aware comparison of one fp32 field of all particles (shape (n,) or (n, k)).
 
     SPH sums cancel (opposing neighbours), so element-wise relative error is meaningless near
     equilibrium; the gate is:
       * identical NaN / Inf pattern,
       * max|got - want| <= tol * max|want|                      (norm-relative),
-      * |got - want| <= tol * (|want| + rms(want)) element-wise.
+      * |got - want| <= tol * (|want| + rms(want)) element-wise, or, when `scale` is given
+        (oracle.force_scale: the sum of |terms| behind each force component, i.e. the
+        conditioning of that sum), |got - want| <= tol * scale element-wise.
+    `elementwise=False` keeps the two norm gates only (whole-step checks, where the inputs of
+    the later passes already differ by the earlier passes' rounding).
     """
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
@@ -61,8 +65,16 @@ def assert_field_close(got, want, name, tol=REL_TOL):
         return 0.0
     rel = err.max() / scale
     assert rel <= tol, f"{name}: norm-relative error {rel:.3e} > {tol}"
-    rms = np.sqrt(np.mean(w * w))
-    bound = tol * (np.abs(w) + rms)
+    l2 = np.sqrt(np.sum(err * err) / np.sum(w * w))
+    assert l2 <= tol, f"{name}: L2-relative error {l2:.3e} > {tol}"
+    if not elementwise:
+        return rel
+    if scale is not None:
+        bound = tol * np.maximum(np.asarray(scale, np.float64)[ok], np.abs(w))
+    else:
+        rms = np.sqrt(np.mean(w * w))
+        bound = tol * (np.abs(w) + rms)
+    bound = np.maximum(bound, np.finfo(np.float32).tiny)
     worst = (err / bound).max()
     assert worst <= 1.0, f"{name}: element-wise error {worst:.3f}x the bound"
     return rel
