@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- SPH particle-updates/s of libnprsph on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # reference algorithm on host cores
+
+One "step" = one pass of the hot path (grid maintenance + rho/pressure + force + integrate,
+i.e. display()'s compute block, Main.cpp:291-305) over every particle of the workload.
+Workload: the 16,777,216-particle fp32 dam break (BASELINE.json configs[2], the configuration
+the HBM-roofline headline is quoted on), 256^3 lattice block, stable parameter recipe of
+SURVEY.md 8(d), seeded jitter.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SPH particle-updates/s (rho+force+integrate)"
+UNIT = "particle-updates/s"
+# algorithmic (compulsory) bytes per particle per launch, SURVEY.md 8(d) / DESIGN.md
+ALGO_BYTES = {"rho": 32, "force": 64, "integrate": 96}
+KERNEL_OF_STAGE = {"rho": "k_rho", "force": "k_force", "integrate": "k_integrate",
+                   "sort": "k_onesweep(+k_radix_hist)", "reorder": "k_reorder_cells(+k_fill_gaps)",
+                   "keys": "k_keys"}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=256, help="lattice block is side^3 particles per GPU")
+    ap.add_argument("--subdiv", type=int, default=2, help="grid cells per smoothing length")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def relaunch_under_torchrun(args):
+    """`python bench.py --gpus N` (N>1) typed by hand: start one rank per GPU ourselves."""
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.abspath(__file__)] + sys.argv[1:]
+    sys.exit(subprocess.call(cmd))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import nprsph_b200 as sph
+    from oracle import oracle as O   # only for the parameter recipe and the cpu_baseline leg
+
+    rank, local, world = dist_env()
+    if args.gpus > 1 and world == 1:
+        relaunch_under_torchrun(args)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libnprsph has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    side = args.side
+    n_local = side ** 3
+    p = O.dam_break_params(side, side, side)
+    stream = torch.cuda.Stream(device=local)
+    sim = sph.Simulation(device=local, stream=stream.cuda_stream, cell_subdiv=args.subdiv)
+    sim.apply_oracle_params(p)
+    sim.scene_block(side, side, side, 0.005, None, 1e-4 * 0.005, 1234)
+    sim.set_paused(False)
+    st = sim.stats()
+    launches_per_step = 6 + st.sort_passes    # hist + P onesweep + reorder + fill + rho + force + integrate
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(args.warmup, 3)
+    with torch.cuda.stream(stream):
+        sim.step(warm)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sim.step(args.steps)
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = n_local * world * args.steps / (ms_total * 1e-3)
+
+    # per-kernel device times (CUDA events between stages on the same stream), live
+    prof = sim.profile_step(max(3, min(args.steps, 10)))
+    stage = max(ALGO_BYTES, key=lambda k: prof[k])
+    peak, peak_src = peaks()
+    achieved = ALGO_BYTES[stage] * n_local / (prof[stage] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        key = f"{KERNEL_OF_STAGE[stage]}@{n_local}@subdiv{args.subdiv}"
+        traffic = tj.get(key)
+    roofline = {"kernel": KERNEL_OF_STAGE[stage], "bound": "hbm", "achieved": round(achieved, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": ALGO_BYTES[stage],
+                "kernel_ms": round(prof[stage], 4),
+                "per_kernel_ms": {k: round(v, 4) for k, v in prof.items()},
+                "per_kernel_frac": {k: round(ALGO_BYTES[k] * n_local / (prof[k] * 1e-3) / 1e9 / peak, 4)
+                                    for k in ALGO_BYTES},
+                "step_frac": round(192 * n_local / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
+
+    # end to end through the C ABI with HOST buffers: upload -> step -> download, every step
+    nbytes = n_local * 64
+    h_a = torch.empty(n_local * 16, dtype=torch.float32).pin_memory()
+    h_b = torch.empty(n_local * 16, dtype=torch.float32).pin_memory()
+    sim.download_ptr(h_a.data_ptr(), n_local)
+    with torch.cuda.stream(stream):
+        sim.upload_ptr(h_a.data_ptr(), n_local); sim.step(1); sim.download_ptr(h_b.data_ptr(), n_local)
+        barrier()
+        e0.record(stream)
+        src, dst = h_b, h_a
+        for _ in range(args.e2e_steps):
+            sim.upload_ptr(src.data_ptr(), n_local)
+            sim.step(1)
+            sim.download_ptr(dst.data_ptr(), n_local)
+            src, dst = dst, src
+        e1.record(stream)
+        barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_local * world * args.e2e_steps / (float(t.item()) * 1e-3)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
+           "d2h_bytes_per_step": nbytes * world, "steps": args.e2e_steps,
+           "api": "nprsph_upload_particles + nprsph_step(1) + nprsph_download_particles, pinned host buffers"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import numpy as np
+        host = src.numpy().reshape(n_local, 16)      # last downloaded state (carries rho/p)
+        cpu_baseline = cpu_sample(O, np.ascontiguousarray(host), p, budget_s=12.0)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"dam_break_{n_local}_per_gpu_fp32 (side {side}, h=2s, "
+                                      f"stable recipe SURVEY 8(d), jitter seed 1234)",
+                          "particles_total": n_local * world, "cell_subdiv": args.subdiv,
+                          "grid_cells": st.num_cells, "sort_passes": st.sort_passes,
+                          "parallelism": "1 process/GPU" if world == 1 else
+                                         f"{world} independent replicas, one per GPU (no data-path collective)",
+                          "l2": "working set per step (>2 GB) exceeds the 126 MB L2; no flush needed"},
+               "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+               "clocks": clocks}
+        if cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_sample(O, host, p, budget_s):
+    """Reference algorithm (all-pairs j loop, the shaders' own) for a bounded sample of the
+    workload's particles on this box's host cores.  `host` already carries rho/p."""
+    import numpy as np
+    n = len(host)
+    threads = O.num_threads()
+    idx0 = np.linspace(0, n - 1, threads, dtype=np.int32)
+    t0 = time.perf_counter(); O.sample_update(host, p, idx0); dt0 = time.perf_counter() - t0
+    m = int(max(threads, min(4096, budget_s / max(dt0, 1e-6) * threads)))
+    m -= m % threads
+    idx = np.linspace(0, n - 1, m, dtype=np.int32)
+    t0 = time.perf_counter(); O.sample_update(host, p, idx); dt = time.perf_counter() - t0
+    return {"value": m / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle all-pairs update (rho+force+integrate, the reference's O(N) loop per "
+                      f"particle) of {m} evenly spaced particles out of {n}, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """The reference's own algorithm on the host cores: the OpenMP C transcription of the three
+    shaders (oracle/, all-pairs).  The GLSL + Win32 reference cannot be built here,
+    so kind = "port".  Each step updates a bounded sample of the workload's particles."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle as O
+    side = args.side
+    n = side ** 3
+    p = O.dam_break_params(side, side, side)
+    host = O.jitter(O.make_block(side, side, side), 1e-4 * 0.005, 1234)
+    host[:, 12] = p.resting_rho          # rho_j read by the force loop (timing only)
+    threads = O.num_threads()
+    steps, warm = args.steps, max(args.warmup, 1)
+    idx0 = np.linspace(0, n - 1, threads, dtype=np.int32)
+    t0 = time.perf_counter(); O.sample_update(host, p, idx0); dt0 = time.perf_counter() - t0
+    per_step = min(6.0, 150.0 / (steps + warm))
+    m = int(max(threads, per_step / max(dt0, 1e-6) * threads))
+    m -= m % threads
+    idx = np.linspace(0, n - 1, m, dtype=np.int32)
+    for _ in range(warm):
+        O.sample_update(host, p, idx)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.sample_update(host, p, idx)
+    dt = time.perf_counter() - t0
+    value = m * steps / dt
+    sample = (f"{m} evenly spaced particles of the {n}-particle dam break per step, all-pairs "
+              f"rho+force+integrate (oracle/sph_oracle.c), {threads} OpenMP threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"dam_break_{n}_per_gpu_fp32 (side {side}, h=2s, stable recipe SURVEY 8(d), "
+                               f"jitter seed 1234)", "particles_total": n, "algorithm": "all-pairs (reference)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

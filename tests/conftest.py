@@ -37,15 +37,18 @@ REL_TOL = 1e-5
 def assert_field_close(got, want, name, tol=REL_TOL, scale=None, elementwise=True):
     """NaN-aware comparison of one fp32 field of all particles (shape (n,) or (n, k)).
 
-    SPH sums cancel (opposing neighbours), so element-wise relative error is meaningless near
-    equilibrium; the gate is:
-      * identical NaN / Inf pattern,
-      * max|got - want| <= tol * max|want|                      (norm-relative),
-      * |got - want| <= tol * (|want| + rms(want)) element-wise, or, when `scale` is given
-        (oracle.force_scale: the sum of |terms| behind each force component, i.e. the
-        conditioning of that sum), |got - want| <= tol * scale element-wise.
-    `elementwise=False` keeps the two norm gates only (whole-step checks, where the inputs of
-    the later passes already differ by the earlier passes' rounding).
+    SPH sums cancel (opposing neighbours) and the equation of state subtracts two nearly equal
+    densities, so a relative error per element is meaningless near equilibrium.  Every gate is
+    therefore relative to the CONDITIONING SCALE s of the quantity:
+      * density (a sum of positive terms) ........ s = |want|                       (default)
+      * pressure k*(rho - rho0) .................... s = k*(rho + rho0)             (pass `scale`)
+      * force (cancelling sums) .................... s = sum of |terms|             (pass `scale`,
+                                                       oracle.force_scale)
+    Gates:  identical NaN / Inf pattern;
+            max|got-want| <= tol * max(s)   and   ||got-want||_2 <= tol * ||s||_2   (norm gates);
+            |got-want| <= tol * s element-wise (with rms(want) added to s when no scale is given).
+    `elementwise=False` keeps the norm gates only (whole-step checks, where the inputs of the
+    later passes already differ by the earlier passes' rounding).
     """
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
@@ -58,22 +61,23 @@ def assert_field_close(got, want, name, tol=REL_TOL, scale=None, elementwise=Tru
     if not ok.any():
         return 0.0
     g, w = got[ok], want[ok]
-    scale = np.abs(w).max()
     err = np.abs(g - w)
-    if scale == 0.0:
+    if scale is not None:
+        s_el = np.maximum(np.asarray(scale, np.float64)[ok], np.abs(w))
+        s_el = np.where(np.isfinite(s_el), s_el, np.abs(w))
+    else:
+        s_el = np.abs(w)
+    smax = s_el.max()
+    if smax == 0.0:
         assert err.max() == 0.0, f"{name}: expected all zeros, max err {err.max()}"
         return 0.0
-    rel = err.max() / scale
+    rel = err.max() / smax
     assert rel <= tol, f"{name}: norm-relative error {rel:.3e} > {tol}"
-    l2 = np.sqrt(np.sum(err * err) / np.sum(w * w))
+    l2 = np.sqrt(np.sum(err * err) / np.sum(s_el * s_el))
     assert l2 <= tol, f"{name}: L2-relative error {l2:.3e} > {tol}"
     if not elementwise:
         return rel
-    if scale is not None:
-        bound = tol * np.maximum(np.asarray(scale, np.float64)[ok], np.abs(w))
-    else:
-        rms = np.sqrt(np.mean(w * w))
-        bound = tol * (np.abs(w) + rms)
+    bound = tol * (s_el if scale is not None else s_el + np.sqrt(np.mean(w * w)))
     bound = np.maximum(bound, np.finfo(np.float32).tiny)
     worst = (err / bound).max()
     assert worst <= 1.0, f"{name}: element-wise error {worst:.3f}x the bound"
