@@ -228,3 +228,12 @@ def gpu_pass(which: int, P, p, counts=False):
     rc = gpu_lib().oracle_gpu_pass(which, _fp(P), len(P), C.byref(p), _u32(c))
     assert rc == 0, "GPU all-pairs oracle failed"
     return c
+
+
+def gpu_force_scale(P, p) -> np.ndarray:
+    """oracle.force_scale computed by brute force on the GPU (for the 1M-particle test)."""
+    out = np.zeros((len(P), 3), np.float32)
+    rc = gpu_lib().oracle_gpu_pass(2, _fp(P), len(P), C.byref(p),
+                                   out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert rc == 0, "GPU all-pairs oracle failed"
+    return out

@@ -71,7 +71,7 @@ def check_passes(sim, sph, oracle, P, p, cell_subdiv, gpu_oracle=False):
     sim.upload(P)
     sim.pass_force()
     if gpu_oracle:
-        scale = None
+        scale = oracle.gpu_force_scale(P, p)
         c_f = oracle.gpu_pass(1, P, p, counts=True)
     else:
         scale = oracle.force_scale(P, p)
