@@ -14,8 +14,8 @@ outputs are stored.  The fixtures pin oracle/sph_oracle.c (tests/test_oracle_gol
 Fixtures (float32, little endian):
   default_10k.npz   the reference scene exactly (N = 10,000): for steps 0..2 the full input
                     state (pos, vel) and, after each pass, its outputs.
-  small_1000.npz    NUM_PARTICLES re-#defined to 1000 (so dt = 1/1000 as integrate_comp.glsl:33
-                    says) with non-default uniforms and a tight box, 6 steps, full states:
+  small_2000.npz    NUM_PARTICLES re-#defined to 2000 (so dt = 1/2000 as integrate_comp.glsl:33
+                    says) with non-default uniforms and a tight box, 4 steps, full states:
                     exercises the wall clamps on all six faces.
   nan_onset.npz     (--nan-onset, ~25 min) the default scene run until the first NaN appears.
 """
@@ -115,14 +115,14 @@ def gen_default(host):
 
 
 def gen_small(host):
-    n = 1000
+    n = 2000
     shaders = [Shader(read(f), {"NUM_PARTICLES": n}) for f in PASSES]
-    state = initial_block((10, 10, 10), host["radius"])
+    state = initial_block((10, 20, 10), host["radius"])
     rng = np.random.default_rng(20261017)
     state["pos"][:, :3] += rng.uniform(-1e-3, 1e-3, (n, 3)).astype(np.float32)
     state["vel"][:, :3] = rng.normal(0.0, 2.0, (n, 3)).astype(np.float32)
     uniforms = {"mass": 1.3e-4, "smoothing_coeff": 2.5, "visc": 40.0, "resting_rho": 1000.0,
-                "upper": (0.048, 0.050, 0.047, 1.0), "lower": (-0.002, -0.004, -0.003, 1.0)}
+                "upper": (0.048, 0.0945, 0.047, 1.0), "lower": (-0.002, -0.004, -0.003, 1.0)}
     out = {"uniforms": np.array([uniforms[k] for k in ("mass", "smoothing_coeff", "visc", "resting_rho")], np.float32),
            "upper": np.array(uniforms["upper"], np.float32), "lower": np.array(uniforms["lower"], np.float32),
            "num_particles": np.int32(n)}
@@ -139,8 +139,8 @@ def gen_small(host):
             out[f"s{s}_out_pos"] = st["pos"][:, :3].copy()
             out[f"s{s}_out_vel"] = st["vel"][:, :3].copy()
 
-    run_case(shaders, 1, state, uniforms, 6, record)
-    np.savez_compressed(os.path.join(HERE, "small_1000.npz"), **out)
+    run_case(shaders, 2, state, uniforms, 4, record)
+    np.savez_compressed(os.path.join(HERE, "small_2000.npz"), **out)
 
 
 def gen_nan_onset(host, max_steps=70):
