@@ -144,7 +144,7 @@ def run_ours(args):
     p = O.dam_break_params(side, side, side)
     stream = torch.cuda.Stream(device=local)
     sim = sph.Simulation(device=local, stream=stream.cuda_stream, cell_subdiv=args.subdiv)
-    sim.apply_oracle_params(p)
+    sim.apply_params(p)
     sim.scene_block(side, side, side, 0.005, None, 1e-4 * 0.005, 1234)
     sim.set_paused(False)
     st = sim.stats()

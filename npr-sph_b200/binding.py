@@ -204,8 +204,9 @@ class Simulation:
                 setattr(cfg, k, v)
         self._ck(self.lib.nprsph_set_config(self._h, C.byref(cfg)))
 
-    def apply_oracle_params(self, p):
-        """Copy an oracle.Params-like object (same field names) into this context."""
+    def apply_params(self, p):
+        """Copy a parameter record with the reference's field names (mass, smoothing_coeff, ...,
+        upper, lower, particle_radius, gas_const, gravity, damping, dt, pi) into this context."""
         self.set_constants(p.mass, p.smoothing_coeff, p.visc, p.resting_rho)
         self.set_boundary(list(p.upper), list(p.lower))
         self.set_config(particle_radius=p.particle_radius, gas_const=p.gas_const,

@@ -8,7 +8,7 @@ subdiv = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 p = O.dam_break_params(n1, n1, n1)
 sim = sph.Simulation(cell_subdiv=subdiv)
-sim.apply_oracle_params(p)
+sim.apply_params(p)
 sim.scene_block(n1, n1, n1, 0.005, None, 1e-4 * 0.005, 1234)
 sim.set_paused(False)
 sim.step(steps)

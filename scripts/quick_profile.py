@@ -10,7 +10,7 @@ def run(n1, subdiv, steps=10, coeff=2.0):
     p = O.dam_break_params(nx, ny, nz)
     p.smoothing_coeff = coeff
     sim = sph.Simulation(cell_subdiv=subdiv)
-    sim.apply_oracle_params(p)
+    sim.apply_params(p)
     sim.scene_block(nx, ny, nz, 0.005, None, 1e-4 * 0.005, 1234)
     sim.set_paused(False)
     sim.step(5); sim.sync()

@@ -26,7 +26,7 @@ def assert_bits_equal(got, want, msg):
 def make_sim(sph, p, cell_subdiv=1, counts=True):
     sim = sph.Simulation(cell_subdiv=cell_subdiv,
                          flags=sph.FLAG_COUNT_NEIGHBOURS if counts else 0)
-    sim.apply_oracle_params(p)
+    sim.apply_params(p)
     return sim
 
 

@@ -1,0 +1,83 @@
+"""Self-consistency of the CPU oracle (no GPU): known answers of SURVEY.md Appendix C, the
+grid-accelerated variant against the literal all-pairs loops, and the sqrt-free predicate."""
+import numpy as np
+import pytest
+
+
+def test_appendix_c_known_answers(oracle):
+    p = oracle.default_params()
+    P = oracle.make_block(10, 100, 10)
+    c = oracle.pass_rho(P, p, counts=True)
+    rho = P[:, 12]
+    assert (c.min(), c.max()) == (51, 253) and c.mean() == pytest.approx(181.2, abs=0.05)
+    assert rho.min() == pytest.approx(44329.7, rel=1e-6)
+    assert rho.mean() == pytest.approx(130256.5, rel=1e-6)
+    assert rho.max() == pytest.approx(160000.0, rel=1e-6)
+    oracle.pass_force(P, p)
+    assert P[:, 13].max() == pytest.approx(3.18e8, rel=1e-3)
+    assert np.abs(P[:, 8:11]).max() == pytest.approx(1.99e10, rel=1e-2)
+    oracle.pass_integrate(P, p)
+    assert np.abs(P[:, 4:7]).max() == pytest.approx(20.6, rel=1e-2)
+
+
+def test_first_nan_at_step_50(oracle):
+    p = oracle.default_params()
+    P = oracle.make_block(10, 100, 10)
+    for s in range(51):
+        assert not np.isnan(P).any(), s
+        oracle.step(P, p, 1)
+    bad = np.nonzero(np.isnan(P[:, :3]).any(axis=1))[0]
+    assert list(bad) == [0, 10]
+
+
+@pytest.mark.parametrize("cell_subdiv", [1, 2, 3])
+def test_grid_variant_is_bit_identical_to_all_pairs(oracle, cell_subdiv):
+    p = oracle.dam_break_params(12, 16, 10)
+    A = oracle.jitter(oracle.make_block(12, 16, 10), 0.4 * 0.005, seed=77)
+    A[5, 0] = np.nan
+    A[6, :3] = A[7, :3]
+    B = A.copy()
+    for _ in range(3):
+        ca = oracle.pass_rho(A, p, counts=True)
+        cb = oracle.pass_rho(B, p, counts=True, grid=cell_subdiv)
+        assert np.array_equal(ca, cb)
+        ca = oracle.pass_force(A, p, counts=True)
+        cb = oracle.pass_force(B, p, counts=True, grid=cell_subdiv)
+        assert np.array_equal(ca, cb)
+        oracle.pass_integrate(A, p)
+        oracle.pass_integrate(B, p)
+        assert np.array_equal(A, B, equal_nan=True)
+
+
+def test_r2_threshold_is_the_sqrt_predicate(oracle):
+    """(sqrtf(r2) < h) == (r2 < T) for every fp32 r2 around the threshold."""
+    for h in (0.02, 0.01, 0.0125, 0.035, 1.0, 3e-5, 7.5):
+        h = np.float32(h)
+        T = oracle.r2_threshold(h)
+        r2 = np.float32(T)
+        lo = r2
+        for _ in range(200):
+            lo = np.nextafter(lo, np.float32(0))
+        xs = [lo]
+        for _ in range(400):
+            xs.append(np.nextafter(xs[-1], np.float32(np.inf)))
+        xs = np.array(xs, np.float32)
+        assert np.array_equal(np.sqrt(xs) < h, xs < T)
+
+
+def test_cell_keys_cover_every_neighbour(oracle):
+    """A pair that passes the predicate is never more than `reach` cells apart on any axis."""
+    p = oracle.dam_break_params(10, 10, 10)
+    rng = np.random.default_rng(1)
+    P = np.zeros((4000, 16), np.float32)
+    P[:, :3] = rng.uniform(-0.0025, 0.05, (4000, 3)).astype(np.float32)
+    h = float(oracle.smoothing_length(p))
+    for k in (1, 2):
+        g = oracle.grid_setup(p, k)
+        keys = oracle.cell_keys(P, g).astype(np.int64)
+        cz = keys % g.dim[2]; cy = (keys // g.dim[2]) % g.dim[1]; cx = keys // (g.dim[2] * g.dim[1])
+        d = P[:, None, :3] - P[None, :1000, :3]
+        r = np.sqrt((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2])
+        i, j = np.nonzero(r < np.float32(h))
+        for c in (cx, cy, cz):
+            assert np.abs(c[i] - c[j]).max() <= k
