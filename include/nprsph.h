@@ -80,6 +80,8 @@ typedef struct nprsph_config {
 } nprsph_config;
 
 #define NPRSPH_FLAG_COUNT_NEIGHBOURS 1u  /* passes also record per-particle neighbour counts */
+#define NPRSPH_FLAG_NO_HITMASK 2u        /* force pass re-tests every candidate instead of using the
+                                            density pass's hit bitmask (A/B measurements) */
 
 typedef struct nprsph_stats {
     uint64_t num_particles;

@@ -53,6 +53,8 @@ struct nprsph_ctx {
     uint32_t* counts_rho = nullptr;
     uint32_t* counts_force = nullptr;
     void* sort_ws = nullptr;
+    uint32_t* hitmask = nullptr;        // [HIT_WORDS + 1][cap] neighbour-hit bits, rho -> force
+    bool mask_valid = false;
 
     uint32_t* cell_start = nullptr;
     size_t cell_cap = 0;
@@ -165,6 +167,12 @@ int refresh_params(nprsph_ctx* c) {
     float cell_size;
     if (setup_grid(c, s.h, &g, &cell_size))
         return fail(c, NPRSPH_ERR_INVALID, "cannot build a grid: smoothing length or bounds invalid%s");
+    {   // column cull threshold: h in cell units plus a margin far above the fp32 error of the
+        // cell coordinates (<= 2^-12 cells for <= 2048 cells per axis)
+        const float hc = s.h * g.inv_cell + 1.0f / 256.0f;
+        s.cull2 = hc * hc;
+    }
+    c->mask_valid = false;
     if (memcmp(&g, &c->grid, sizeof g) != 0) { c->keys_valid = false; c->grid_valid = false; }
     const size_t need = (size_t)g.num_cells + 2;
     if (need > c->cell_cap) {
@@ -214,6 +222,7 @@ int ensure_capacity(nprsph_ctx* c, uint64_t n) {
         CK(c, realloc_dev(c->counts_force, n));
     }
     { char* w = (char*)c->sort_ws; CK(c, realloc_dev(w, sort_workspace_bytes(n))); c->sort_ws = w; }
+    if (!(c->cfg.flags & NPRSPH_FLAG_NO_HITMASK)) CK(c, realloc_dev(c->hitmask, n * (HIT_WORDS + 1)));
     c->cap = n;
     c->params_dirty = true;     // gap-list capacity depends on cap
     return NPRSPH_OK;
@@ -248,20 +257,24 @@ int ensure_grid(nprsph_ctx* c, bool with_force, cudaEvent_t* ev /* 4 events or n
     if (ev) CK(c, cudaEventRecord(ev[3], c->stream));
     c->cur = nxt;
     c->grid_valid = true;
+    c->mask_valid = false;
     CK(c, cudaGetLastError());
     return NPRSPH_OK;
 }
 
 int run_rho(nprsph_ctx* c, bool write_pressure) {
     launch_rho(c->pos[c->cur], c->vel[c->cur], write_pressure ? c->frc[c->cur] : nullptr,
-               c->cell_start, (uint32_t)c->n, c->grid, c->sph, c->counts_rho, c->stream);
+               c->cell_start, (uint32_t)c->n, c->grid, c->sph, c->counts_rho, c->hitmask,
+               (uint32_t)c->cap, c->stream);
+    c->mask_valid = c->hitmask != nullptr;
     c->aos_stale = true;
     return NPRSPH_OK;
 }
 
 int run_force(nprsph_ctx* c) {
     launch_force(c->pos[c->cur], c->vel[c->cur], c->frc[c->cur], c->cell_start, (uint32_t)c->n,
-                 c->grid, c->sph, c->counts_force, c->stream);
+                 c->grid, c->sph, c->counts_force, c->mask_valid ? c->hitmask : nullptr,
+                 (uint32_t)c->cap, c->stream);
     c->aos_stale = true;
     return NPRSPH_OK;
 }
@@ -272,6 +285,7 @@ int run_integrate(nprsph_ctx* c) {
                      c->grid, c->sph, c->stream);
     c->keys_valid = true;
     c->grid_valid = false;
+    c->mask_valid = false;
     c->sorted_keys = nullptr;
     c->aos_stale = true;
     return NPRSPH_OK;
@@ -292,6 +306,7 @@ int adopt_aos(nprsph_ctx* c) {
     CK(c, cudaGetLastError());
     c->keys_valid = false;
     c->grid_valid = false;
+    c->mask_valid = false;
     c->aos_stale = false;
     c->sorted_keys = nullptr;
     return NPRSPH_OK;
@@ -429,7 +444,7 @@ int nprsph_destroy(nprsph_ctx* c) {
         cudaFree(c->pos[b]); cudaFree(c->vel[b]); cudaFree(c->frc[b]);
         cudaFree(c->keys[b]); cudaFree(c->vals[b]);
     }
-    cudaFree(c->counts_rho); cudaFree(c->counts_force); cudaFree(c->sort_ws);
+    cudaFree(c->counts_rho); cudaFree(c->counts_force); cudaFree(c->sort_ws); cudaFree(c->hitmask);
     cudaFree(c->cell_start); cudaFree(c->gap_list); cudaFree(c->gap_count);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -464,8 +479,8 @@ int nprsph_set_config(nprsph_ctx* c, const nprsph_config* cfg) {
     if (!config_ok(cfg)) return fail(c, NPRSPH_ERR_INVALID, "bad nprsph_config%s");
     if (cfg->device != c->cfg.device || cfg->stream != c->cfg.stream)
         return fail(c, NPRSPH_ERR_INVALID, "device and stream are fixed at create time%s");
-    if ((cfg->flags ^ c->cfg.flags) & NPRSPH_FLAG_COUNT_NEIGHBOURS)
-        return fail(c, NPRSPH_ERR_INVALID, "NPRSPH_FLAG_COUNT_NEIGHBOURS is fixed at create time%s");
+    if (cfg->flags != c->cfg.flags)
+        return fail(c, NPRSPH_ERR_INVALID, "flags are fixed at create time%s");
     c->cfg = *cfg;
     if (c->cfg.cell_subdiv == 0) c->cfg.cell_subdiv = 1;
     c->params_dirty = true;

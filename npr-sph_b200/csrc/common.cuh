@@ -7,6 +7,9 @@
 
 namespace nprsph {
 
+// words of neighbour-hit bits handed from the density pass to the force pass (+1 control word)
+constexpr uint32_t HIT_WORDS = 7;
+
 // Uniform-grid definition (DESIGN.md "Grid").  The same arithmetic is restated in
 // oracle/sph_oracle.c:oracle_grid_setup / cell_key so keys can be compared bit-exactly.
 struct GridDev {
@@ -24,6 +27,7 @@ struct SphDev {
     float h;            // smoothing_coeff * particle_radius   (rho_pres_comp.glsl:40)
     float h2;           // h*h
     float r2_max;       // smallest t with sqrt_rn(t) >= h  =>  (length(d) < h) == (r2 < r2_max)
+    float cull2;        // (h in cell units + rounding margin)^2: column-footprint cull threshold
     float rho_coef;     // mass*315 / (64*pi*h^9)             (rho_pres_comp.glsl:52)
     float pres_coef;    // -mass*spiky/2 = mass*45/(2*pi*h^6) (force_comp.glsl:41,59)
     float visc_coef;    // visc*mass*laplacian                (force_comp.glsl:42,60,63)

@@ -22,10 +22,12 @@ void launch_slot_ids(const float4* posid, uint32_t* ids, uint32_t n, cudaStream_
 // sph_passes.cu
 void launch_rho(const float4* posid, float4* velrho, float4* forcep_or_null,
                 const uint32_t* cell_start, uint32_t n, const GridDev& g, const SphDev& sp,
-                uint32_t* counts_by_id, cudaStream_t st);
+                uint32_t* counts_by_id, uint32_t* hitmask_or_null, uint32_t mask_stride,
+                cudaStream_t st);
 void launch_force(const float4* posid, const float4* velrho, float4* forcep,
                   const uint32_t* cell_start, uint32_t n, const GridDev& g, const SphDev& sp,
-                  uint32_t* counts_by_id, cudaStream_t st);
+                  uint32_t* counts_by_id, const uint32_t* hitmask_or_null, uint32_t mask_stride,
+                  cudaStream_t st);
 void launch_integrate(float4* posid, float4* velrho, const float4* forcep, uint32_t* keys,
                       uint32_t n, const GridDev& g, const SphDev& sp, cudaStream_t st);
 

@@ -56,13 +56,12 @@ k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int passes, int key_
             for (int v = 0; v < HIST_ITEMS; v++)
                 if (first + v < n) { k[v] = keys[first + v]; cnt = v + 1; }
         }
-        if (cnt == 0) continue;
         for (int p = 0; p < passes; p++) {
             const int shift = p * RADIX_BITS;
             const int bits = key_bits - shift;
             const uint32_t mask = bits >= RADIX_BITS ? (uint32_t)(RADIX - 1) : ((1u << bits) - 1u);
-            uint32_t run_d = (k[0] >> shift) & mask;
-            uint32_t run = 1;
+            uint32_t run_d = cnt ? ((k[0] >> shift) & mask) : 0xFFFFFFFFu;
+            uint32_t run = cnt ? 1u : 0u;
 #pragma unroll
             for (int v = 1; v < HIST_ITEMS; v++) {
                 if (v < cnt) {
@@ -71,7 +70,15 @@ k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int passes, int key_
                     run++;
                 }
             }
-            atomicAdd(&sh[p][run_d], run);
+            // the pending run: one atomic per warp when the whole warp ended on the same digit
+            // (the usual case for the high digits of cell-ordered keys), else one per thread
+            const uint32_t d0 = __shfl_sync(0xffffffffu, run_d, 0);
+            if (__all_sync(0xffffffffu, run_d == d0)) {
+                const uint32_t total = __reduce_add_sync(0xffffffffu, run);
+                if ((threadIdx.x & 31) == 0 && total) atomicAdd(&sh[p][d0], total);
+            } else if (run) {
+                atomicAdd(&sh[p][run_d], run);
+            }
         }
     }
     __syncthreads();
@@ -132,18 +139,26 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     }
 
     // stable rank of every key among the keys of its warp with the same digit
+    // All match-any votes are issued first (independent), then one shared-memory atomic per
+    // distinct digit per row (by the lowest peer lane) claims the rank base, which is broadcast
+    // back with a shuffle.  Atomics of one warp to one address retire in program order, so row k
+    // ranks below row k+1: the sort stays stable, and the 16 rows overlap instead of forming one
+    // load -> store dependency chain.
     uint32_t rank[SORT_ITEMS];
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* my_hist = s_warp_hist[warp];
+    uint32_t peers[SORT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++)
+        peers[k] = __match_any_sync(0xffffffffu, (key[k] >> shift) & mask);
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; k++) {
         const uint32_t d = (key[k] >> shift) & mask;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t prev = my_hist[d];
-        __syncwarp();
-        if ((peers & lt_mask) == 0) my_hist[d] = prev + __popc(peers);
-        __syncwarp();
-        rank[k] = prev + __popc(peers & lt_mask);
+        const uint32_t below = peers[k] & lt_mask;
+        uint32_t base = 0;
+        if (below == 0) base = atomicAdd(&my_hist[d], (uint32_t)__popc(peers[k]));
+        base = __shfl_sync(0xffffffffu, base, __ffs(peers[k]) - 1);
+        rank[k] = base + __popc(below);
     }
     __syncthreads();
 
