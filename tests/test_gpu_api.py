@@ -1,0 +1,164 @@
+"""Drop-in semantics of the C ABI against the reference's host code (Main.cpp): pause / reset
+('p' / 'r', Main.cpp:454-476), parameter upload (sendUniforms, Main.cpp:274-278), buffer
+ownership and the error model."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_starts_paused_and_p_toggles(sph, oracle):
+    """`bool simulate;` is zero-initialised (Main.cpp:87): dispatches are skipped until 'p'."""
+    sim = sph.Simulation()
+    P0 = oracle.make_block(10, 100, 10)
+    assert sim.paused and sim.num_particles == 10000
+    sim.step(5)
+    assert np.array_equal(sim.download(), P0) and sim.stats().steps_done == 0
+    sim.toggle_pause()
+    assert not sim.paused
+    sim.step(2)
+    moved = sim.download()
+    assert sim.stats().steps_done == 2 and not np.array_equal(moved[:, :3], P0[:, :3])
+    sim.toggle_pause()                      # pause again: state frozen, rendering would continue
+    sim.step(3)
+    assert np.array_equal(sim.download(), moved)
+
+
+def test_r_resets_particles_but_keeps_pause_flag_and_constants(sph, oracle):
+    """'r' = init_particles() + reload_shader(): pause flag and GUI constants persist (Main.cpp:460-464)."""
+    sim = sph.Simulation()
+    sim.set_constants(mass=0.03, visc=2500.0)
+    sim.set_paused(False)
+    sim.step(3)
+    sim.reset()
+    assert not sim.paused, "reset while running keeps running"
+    c = sim.get_constants()
+    assert c.mass == pytest.approx(0.03) and c.visc == pytest.approx(2500.0)
+    assert np.array_equal(sim.download(), oracle.make_block(10, 100, 10))
+    # and the next step uses the persisted constants
+    p = oracle.default_params()
+    p.mass, p.visc = 0.03, 2500.0
+    P = oracle.make_block(10, 100, 10)
+    oracle.step(P, p, 1)
+    sim.step(1)
+    G = sim.download()
+    assert np.abs(G[:, 12] - P[:, 12]).max() / P[:, 12].max() < 1e-5
+
+
+def test_reset_restores_the_last_scene_block(sph, oracle):
+    sim = sph.Simulation()
+    sim.scene_block(6, 7, 5, 0.005, (0.01, 0.02, 0.03), 0.0, 0)
+    want = oracle.make_block(6, 7, 5, 0.005, (0.01, 0.02, 0.03))
+    assert np.array_equal(sim.download(), want)
+    sim.set_paused(False)
+    sim.step(2)
+    sim.reset()
+    assert np.array_equal(sim.download(), want)
+    # seeded jitter is reproducible and identical to the oracle's generator
+    sim.scene_block(8, 8, 8, 0.005, None, 2e-4, 99)
+    assert np.array_equal(sim.download(), oracle.jitter(oracle.make_block(8, 8, 8), 2e-4, 99))
+
+
+def test_parameter_edits_take_effect_at_the_next_step(sph, oracle):
+    """glBufferSubData of the UBOs (Main.cpp:274-278) is seen by the next dispatches."""
+    p = oracle.dam_break_params(8, 8, 8)
+    P = oracle.make_block(8, 8, 8)
+    sim = sph.Simulation()
+    sim.apply_params(p)
+    sim.upload(P)
+    sim.set_paused(False)
+    sim.step(1)
+    oracle.step(P, p, 1)
+    # change h (forces a new grid), mass and the box between steps
+    p.smoothing_coeff, p.mass = 2.6, 1.5e-4
+    p.upper[1] = 0.03
+    sim.set_constants(smoothing_coeff=2.6, mass=1.5e-4)
+    sim.set_boundary(list(p.upper), list(p.lower))
+    sim.step(1)
+    oracle.step(P, p, 1)
+    G = sim.download()
+    assert (G[:, 1] <= np.float32(0.03)).all()
+    assert np.abs(G[:, 12] - P[:, 12]).max() / P[:, 12].max() < 1e-5
+    assert np.abs(G[:, :3] - P[:, :3]).max() < 1e-6
+
+
+def test_upload_download_roundtrip_and_device_pointer(sph):
+    rng = np.random.default_rng(0)
+    rec = rng.normal(size=(1234, 16)).astype(np.float32)
+    rec[:, :3] = np.abs(rec[:, :3]) * 0.01
+    sim = sph.Simulation()
+    sim.upload(rec)
+    assert sim.num_particles == 1234
+    assert np.array_equal(sim.download(), rec)           # untouched until a pass runs
+    ptr, n = sim.device_particles()
+    assert ptr and n == 1234
+    # structured dtype view of the same 64-byte records
+    rec2 = rec.view(sph.PARTICLE_DTYPE).reshape(-1)
+    sim.upload(rec2)
+    assert np.array_equal(sim.download(), rec)
+
+
+def test_error_model(sph):
+    lib = sph.load()
+    cfg = sph.default_config()
+    cfg.struct_size = 7
+    h = C.c_void_p()
+    assert lib.nprsph_create(C.byref(cfg), C.byref(h)) == sph.ERR_INVALID
+    assert b"nprsph_config" in lib.nprsph_last_error(None)
+    cfg = sph.default_config(device=4096)
+    assert lib.nprsph_create(C.byref(cfg), C.byref(h)) == sph.ERR_INVALID
+    sim = sph.Simulation()
+    with pytest.raises(sph.NprSphError) as ei:
+        sim.step(-1)
+    assert ei.value.code == sph.ERR_INVALID
+    with pytest.raises(sph.NprSphError):
+        sim.set_constants(smoothing_coeff=0.0)
+        sim.set_paused(False)
+        sim.step(1)                                        # h = 0: no grid can be built
+    sim.set_constants(smoothing_coeff=4.0)
+    sim.step(1)                                            # not sticky: works again
+    with pytest.raises(sph.NprSphError) as ei:
+        sim.debug_read(sph.DBG_COUNTS_RHO)                 # FLAG_COUNT_NEIGHBOURS not set
+    assert ei.value.code == sph.ERR_STATE
+    # GL presenter without a current GL context: a clean error, not a crash
+    assert lib.nprsph_gl_register(sim._h, 1) == sph.ERR_UNSUPPORTED
+    assert lib.nprsph_gl_publish(sim._h) == sph.ERR_STATE
+    assert lib.nprsph_gl_unregister(sim._h) == sph.OK
+    sim.step(1)
+
+
+def test_hitmask_and_rescan_force_paths_agree(sph, oracle):
+    """The force pass driven by the density pass's hit bitmask must give the same neighbour sets
+    (counts bit-exact) and forces as the pass that re-tests every candidate."""
+    nx = 24
+    p = oracle.dam_break_params(nx, nx, nx)
+    P = oracle.jitter(oracle.make_block(nx, nx, nx), 0.2 * 0.005, seed=3)
+    out = []
+    for flags in (sph.FLAG_COUNT_NEIGHBOURS, sph.FLAG_COUNT_NEIGHBOURS | sph.FLAG_NO_HITMASK):
+        sim = sph.Simulation(cell_subdiv=2, flags=flags)
+        sim.apply_params(p)
+        sim.upload(P)
+        sim.set_paused(False)
+        sim.step(4)
+        sim.pass_rho()
+        sim.pass_force()
+        out.append((sim.download(), sim.debug_read(sph.DBG_COUNTS_FORCE)))
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][0], out[1][0]), "same arithmetic in the same order: bit-identical"
+
+
+def test_dense_clump_overflows_the_hitmask_gracefully(sph, oracle):
+    """More candidates than the bitmask holds (reference default scene: ~1700 per particle with
+    h = 4s at 160x rest density) must fall back to the re-test path with identical results."""
+    p = oracle.default_params()
+    P = oracle.make_block(10, 100, 10)
+    sim = sph.Simulation(cell_subdiv=2, flags=sph.FLAG_COUNT_NEIGHBOURS)
+    sim.upload(P)
+    sim.pass_rho()
+    sim.pass_force()
+    c = oracle.pass_rho(P, p, counts=True)
+    cf = oracle.pass_force(P, p, counts=True)
+    assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_RHO), c)
+    assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_FORCE), cf)
