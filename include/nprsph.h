@@ -185,6 +185,49 @@ int nprsph_gl_register(nprsph_ctx* ctx, unsigned int gl_buffer);
 int nprsph_gl_publish(nprsph_ctx* ctx);
 int nprsph_gl_unregister(nprsph_ctx* ctx);
 
+/* ---- multi-GPU: 1-D slab decomposition along x, ONE context per GPU -------------
+ * No reference counterpart (single GL context, Main.cpp:668-680).  Rank r owns the particles whose
+ * global x cell index is in [x_begin, x_end); every step it exchanges `reach` cell layers of ghost
+ * particles with its two neighbours and hands over the particles that crossed a slab face.
+ * NCCL transport: one process per GPU, ncclSend/ncclRecv on the context's stream.  LOCAL transport:
+ * all ranks are contexts of one process on one stream (lets a single GPU run the whole protocol). */
+#define NPRSPH_TRANSPORT_NCCL 0
+#define NPRSPH_TRANSPORT_LOCAL 1
+
+typedef struct nprsph_dist_config {
+    uint32_t struct_size;       /* = sizeof(nprsph_dist_config) */
+    int32_t  rank, world;
+    int32_t  transport;         /* NPRSPH_TRANSPORT_* */
+    uint8_t  nccl_id[128];      /* ncclUniqueId made by nprsph_dist_unique_id() on one rank */
+    uint64_t max_own;           /* capacities in particles; 0 = derived from the scene */
+    uint64_t max_ghost;         /* per side */
+    uint64_t max_migrate;       /* per side and step */
+} nprsph_dist_config;
+
+typedef struct nprsph_dist_info {
+    int32_t  rank, world;
+    int32_t  x_begin, x_end;    /* owned global x cell range */
+    uint64_t num_own, ghosts_left, ghosts_right, nan_particles;
+    uint64_t migrated_total, steps_done, cap_own, cap_ghost;
+} nprsph_dist_info;
+
+/* count-balanced slab boundaries from a per-x-plane particle histogram (pure host code):
+ * bounds[0] = 0 <= ... <= bounds[world] = dimx, every slab at least min_width cells wide */
+int nprsph_slab_partition(const uint64_t* hist, int dimx, int world, int min_width, int32_t* bounds);
+int nprsph_dist_unique_id(uint8_t id[128]);
+int nprsph_dist_init(nprsph_ctx* ctx, const nprsph_dist_config* cfg);
+int nprsph_dist_link_local(nprsph_ctx** ranks, int n);
+/* collective: every rank passes the same GLOBAL block and keeps the particles of its slab
+ * (original index = index in the global block, as in make_grid(), Main.cpp:488-505) */
+int nprsph_dist_scene_block(nprsph_ctx* ctx, int nx, int ny, int nz, float spacing,
+                            const float origin[3], float jitter, uint32_t seed);
+/* collective step.  NCCL: ranks = {ctx}, n_local = 1.  LOCAL: all ranks in rank order. */
+int nprsph_dist_step(nprsph_ctx** ranks, int n_local, int steps);
+/* collective; copies the own particles of ranks[which] (records + their global indices) */
+int nprsph_dist_download(nprsph_ctx** ranks, int n_local, int which, nprsph_particle* records,
+                         uint32_t* ids, uint64_t capacity, uint64_t* n_out);
+int nprsph_dist_get_info(nprsph_ctx* ctx, nprsph_dist_info* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,18 @@ SYMBOLS = {
     "nprsph_gl_register": (C.c_int, [_P, C.c_uint]),
     "nprsph_gl_publish": (C.c_int, [_P]),
     "nprsph_gl_unregister": (C.c_int, [_P]),
+    # multi-GPU (slab decomposition); the Python-side driver lives in dist.py
+    "nprsph_slab_partition": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(C.c_int32)]),
+    "nprsph_dist_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "nprsph_dist_init": (C.c_int, [_P, _P]),
+    "nprsph_dist_link_local": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "nprsph_dist_scene_block": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float,
+                                          C.POINTER(C.c_float), C.c_float, C.c_uint32]),
+    "nprsph_dist_step": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
+    "nprsph_dist_download": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, C.c_uint64,
+                                       C.POINTER(C.c_uint64)]),
+    "nprsph_dist_get_info": (C.c_int, [_P, _P]),
 }
 
 _lib = None

@@ -4,17 +4,12 @@
 // (Main.cpp:510-539,631-641), the per-frame dispatch block (Main.cpp:291-305), parameter
 // upload (Main.cpp:274-278) and the p/r keys (Main.cpp:454-476).  Everything runs on one CUDA
 // stream; there is no CPU implementation of any pass behind this API.
-#include "../../include/nprsph.h"
-
 #include <math.h>
-#include <stdio.h>
 #include <string.h>
 
 #include <new>
-#include <string>
 
-#include "kernels.cuh"
-#include "sort.cuh"
+#include "context.cuh"
 
 using namespace nprsph;
 
@@ -27,57 +22,9 @@ namespace {
 thread_local std::string g_create_error;
 }
 
-struct nprsph_ctx {
-    nprsph_config cfg;
-    nprsph_constants consts;
-    nprsph_boundary bounds;
-    int num_sms = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    bool paused = true;                 // `bool simulate;` starts false, Main.cpp:87
-    std::string err;
-    int sticky = 0;
+namespace nprsph {
 
-    struct { int nx, ny, nz; float spacing, origin[3], jitter; uint32_t seed; } scene;
-
-    uint64_t n = 0, cap = 0;
-    void* aos = nullptr;                // Particle[n], original order (SSBO binding 0)
-    float4* pos[2] = {nullptr, nullptr};
-    float4* vel[2] = {nullptr, nullptr};
-    float4* frc[2] = {nullptr, nullptr};
-    int cur = 0;
-    uint32_t* keys[2] = {nullptr, nullptr};
-    uint32_t* vals[2] = {nullptr, nullptr};
-    uint32_t* sorted_keys = nullptr;
-    uint32_t* last_perm = nullptr;
-    uint32_t* counts_rho = nullptr;
-    uint32_t* counts_force = nullptr;
-    void* sort_ws = nullptr;
-    uint32_t* hitmask = nullptr;        // [HIT_WORDS + 1][cap] neighbour-hit bits, rho -> force
-    bool mask_valid = false;
-
-    uint32_t* cell_start = nullptr;
-    size_t cell_cap = 0;
-    uint4* gap_list = nullptr;
-    size_t gap_cap = 0;
-    uint32_t* gap_count = nullptr;      // also scratch for the NaN counter (8 bytes)
-
-    GridDev grid;
-    SphDev sph;
-    float cell_size = 0.f;
-    int key_bits = 1;
-    bool params_dirty = true;
-    bool keys_valid = false;
-    bool grid_valid = false;
-    bool aos_stale = false;             // SoA state is newer than the AoS view
-    uint64_t steps_done = 0;
-
-    cudaGraphicsResource* gl_res = nullptr;
-};
-
-namespace {
-
-int fail(nprsph_ctx* c, int code, const char* fmt, const char* detail = "") {
+int fail(nprsph_ctx* c, int code, const char* fmt, const char* detail) {
     char buf[512];
     snprintf(buf, sizeof buf, fmt, detail);
     if (c) { c->err = buf; if (code == NPRSPH_ERR_CUDA) c->sticky = code; }
@@ -85,19 +32,9 @@ int fail(nprsph_ctx* c, int code, const char* fmt, const char* detail = "") {
     return code;
 }
 
-#define CK(ctx, call)                                                                     \
-    do {                                                                                  \
-        cudaError_t e_ = (call);                                                          \
-        if (e_ != cudaSuccess) return fail((ctx), NPRSPH_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
-    } while (0)
+}  // namespace nprsph
 
-#define GUARD(ctx)                                                                        \
-    do {                                                                                  \
-        if (!(ctx)) return NPRSPH_ERR_INVALID;                                            \
-        if ((ctx)->sticky) return (ctx)->sticky;                                          \
-        cudaError_t e_ = cudaSetDevice((ctx)->cfg.device);                                \
-        if (e_ != cudaSuccess) return fail((ctx), NPRSPH_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e_)); \
-    } while (0)
+namespace {
 
 // Smallest fp32 t with sqrtf(t) >= h  (so `length(d) < h` == `r2 < t`; sqrtf is monotone).
 float r2_threshold(float h) {
@@ -138,11 +75,15 @@ int setup_grid(const nprsph_ctx* c, float h, GridDev* g, float* cell_size) {
     g->inv_cell = (float)(1.0 / cell);
     g->reach = k;
     g->num_cells = (uint32_t)((int64_t)g->dim[0] * g->dim[1] * g->dim[2]);
+    g->x_off = 0;
+    g->dimx_global = g->dim[0];
     *cell_size = (float)cell;
     return 0;
 }
 
-int refresh_params(nprsph_ctx* c) {
+}  // namespace
+
+int nprsph::refresh_params(nprsph_ctx* c) {
     if (!c->params_dirty) return NPRSPH_OK;
     const nprsph_config& cf = c->cfg;
     SphDev s;
@@ -198,11 +139,7 @@ int refresh_params(nprsph_ctx* c) {
     return NPRSPH_OK;
 }
 
-template <typename T>
-cudaError_t realloc_dev(T*& p, size_t count) {
-    if (p) { cudaError_t e = cudaFree(p); p = nullptr; if (e != cudaSuccess) return e; }
-    return count ? cudaMalloc(&p, count * sizeof(T)) : cudaSuccess;
-}
+namespace {
 
 int ensure_capacity(nprsph_ctx* c, uint64_t n) {
     if (n >= (1ull << 30)) return fail(c, NPRSPH_ERR_INVALID, "at most 2^30-1 particles per context%s");
@@ -264,7 +201,7 @@ int ensure_grid(nprsph_ctx* c, bool with_force, cudaEvent_t* ev /* 4 events or n
 
 int run_rho(nprsph_ctx* c, bool write_pressure) {
     launch_rho(c->pos[c->cur], c->vel[c->cur], write_pressure ? c->frc[c->cur] : nullptr,
-               c->cell_start, (uint32_t)c->n, c->grid, c->sph, c->counts_rho, c->hitmask,
+               c->cell_start, 0u, (uint32_t)c->n, c->grid, c->sph, c->counts_rho, c->hitmask,
                (uint32_t)c->cap, c->stream);
     c->mask_valid = c->hitmask != nullptr;
     c->aos_stale = true;
@@ -272,7 +209,7 @@ int run_rho(nprsph_ctx* c, bool write_pressure) {
 }
 
 int run_force(nprsph_ctx* c) {
-    launch_force(c->pos[c->cur], c->vel[c->cur], c->frc[c->cur], c->cell_start, (uint32_t)c->n,
+    launch_force(c->pos[c->cur], c->vel[c->cur], c->frc[c->cur], c->cell_start, 0u, (uint32_t)c->n,
                  c->grid, c->sph, c->counts_force, c->mask_valid ? c->hitmask : nullptr,
                  (uint32_t)c->cap, c->stream);
     c->aos_stale = true;
@@ -439,6 +376,7 @@ int nprsph_destroy(nprsph_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->gl_res) cudaGraphicsUnregisterResource(c->gl_res);
+    if (c->dist) dist_destroy(c);
     cudaFree(c->aos);
     for (int b = 0; b < 2; b++) {
         cudaFree(c->pos[b]); cudaFree(c->vel[b]); cudaFree(c->frc[b]);

@@ -18,6 +18,11 @@ struct GridDev {
     int   dim[3];
     int   reach;          // cells walked on each side of the home cell
     uint32_t num_cells;   // sentinel key (NaN positions) == num_cells
+    // Slab decomposition (multi-GPU): dim[0] is the LOCAL number of x cells (own slab plus `reach`
+    // ghost layers on each side), x_off the global x index of local cell 0 and dimx_global the
+    // global number of x cells.  Single GPU: x_off = 0, dimx_global = dim[0].
+    int   x_off;
+    int   dimx_global;
 };
 
 // Run-time constants of the three passes.  Sources: ConstantsUniform / BoundaryUniform
@@ -53,9 +58,19 @@ __device__ __forceinline__ bool pos_is_nan(float x, float y, float z) {
     return (x != x) || (y != y) || (z != z);
 }
 
+// local x cell index; the global index is computed first so that every rank assigns a particle
+// to the same global cell bit for bit.  May fall outside [0, dim[0]) for a particle that left
+// the slab.
+__device__ __forceinline__ int cell_x_unclamped(float x, const GridDev& g) {
+    return cell_coord(x, g.lo[0], g.inv_cell, g.dimx_global) - g.x_off;
+}
+__device__ __forceinline__ int cell_x(float x, const GridDev& g) {
+    return min(max(cell_x_unclamped(x, g), 0), g.dim[0] - 1);
+}
+
 __device__ __forceinline__ uint32_t cell_key(float x, float y, float z, const GridDev& g) {
     if (pos_is_nan(x, y, z)) return g.num_cells;
-    const int cx = cell_coord(x, g.lo[0], g.inv_cell, g.dim[0]);
+    const int cx = cell_x(x, g);
     const int cy = cell_coord(y, g.lo[1], g.inv_cell, g.dim[1]);
     const int cz = cell_coord(z, g.lo[2], g.inv_cell, g.dim[2]);
     return ((uint32_t)cx * (uint32_t)g.dim[1] + (uint32_t)cy) * (uint32_t)g.dim[2] + (uint32_t)cz;

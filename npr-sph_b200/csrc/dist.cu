@@ -1,0 +1,777 @@
+// dist.cu -- multi-GPU step: 1-D slab decomposition along x with ghost-particle halo exchange and
+// particle migration (the reference itself is single-GPU, Main.cpp:668-680).
+//
+// One context (= one process with NCCL, or one "virtual rank" with the in-process LOCAL transport
+// used by the single-GPU tests) owns the particles whose GLOBAL x cell index lies in [X0, X1).
+// Slots are laid out [ghost L | own | ghost R]; because keys are x-major, the particles a
+// neighbour needs as ghosts (the first / last `reach` x layers of the slab) are contiguous slot
+// ranges of the sorted own array, so halo messages are sent straight out of and received
+// straight into the particle arrays (no pack / unpack kernels).  Per step:
+//
+//   classify   own keys -> leavers copied to the migration buffers, boundary-layer counts
+//   exchange   8 counters with both neighbours, ONE host sync; every later size is known
+//   exchange   migrants; append immigrants (ordered by particle id) behind the own particles
+//   sort       (key, slot) with the onesweep sort; leavers carry a sentinel key and drop off
+//   exchange   boundary-layer positions -> ghost slots; ghost keys; cell table over all slots
+//   k_rho      own slots
+//   exchange   boundary-layer (velocity, rho)
+//   k_force, k_integrate (+ next keys; a particle that left the slab gets GONE_L / GONE_R)
+#include "dist.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <new>
+
+using namespace nprsph;
+
+namespace {
+
+// ---- NCCL through dlopen: no link-time dependency for single-GPU users --------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        // a libnccl.so.2 that is already loaded (e.g. torch's bundled copy) is reused by soname
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) {
+#define NCCL_SYM(field, name) *(void**)(&api.field) = dlsym(api.lib, name)
+            NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+            NCCL_SYM(CommInitRank, "ncclCommInitRank");
+            NCCL_SYM(CommDestroy, "ncclCommDestroy");
+            NCCL_SYM(Send, "ncclSend");
+            NCCL_SYM(Recv, "ncclRecv");
+            NCCL_SYM(GroupStart, "ncclGroupStart");
+            NCCL_SYM(GroupEnd, "ncclGroupEnd");
+            NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+            if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.GroupStart ||
+                !api.GroupEnd) { dlclose(api.lib); api.lib = nullptr; }
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+
+#define NCK(ctx, call)                                                                     \
+    do {                                                                                   \
+        ncclResult_t r_ = (call);                                                          \
+        if (r_ != ncclSuccess) {                                                           \
+            (ctx)->sticky = NPRSPH_ERR_COMM;                                               \
+            return fail((ctx), NPRSPH_ERR_COMM, #call ": %s",                              \
+                        nccl()->GetErrorString ? nccl()->GetErrorString(r_) : "NCCL error"); \
+        }                                                                                  \
+    } while (0)
+
+constexpr int TPB = 256;
+inline unsigned blocks_for(uint64_t n) { return (unsigned)((n + TPB - 1) / TPB); }
+
+// ---- kernels ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cell_key_slab(float x, float y, float z, const GridDev& g, int W, int R) {
+    if (pos_is_nan(x, y, z)) return g.num_cells;                 // stays on its rank for ever
+    const int cxl = cell_x_unclamped(x, g);
+    if (cxl < R) return g.num_cells + 1u;                        // GONE_L: belongs to the left rank
+    if (cxl >= R + W) return g.num_cells + 2u;                   // GONE_R
+    const int cy = cell_coord(y, g.lo[1], g.inv_cell, g.dim[1]);
+    const int cz = cell_coord(z, g.lo[2], g.inv_cell, g.dim[2]);
+    return ((uint32_t)cxl * (uint32_t)g.dim[1] + (uint32_t)cy) * (uint32_t)g.dim[2] + (uint32_t)cz;
+}
+
+// candidate particles of the global block scene for this rank: lattice planes [i0, i0+ni)
+__device__ __forceinline__ uint32_t hash32(uint32_t seed, uint32_t idx) {
+    uint32_t x = seed ^ (idx * 0x9E3779B9u);
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_slab_scene(float4* __restrict__ posid, float4* __restrict__ velrho, uint32_t* __restrict__ keys,
+             int i0, int ni, int ny, int nz, float spacing, float ox, float oy, float oz,
+             float jitter, uint32_t seed, GridDev g, int W, int R) {
+    const uint64_t n = (uint64_t)ni * ny * nz;
+    const uint64_t t = (uint64_t)blockIdx.x * TPB + threadIdx.x;
+    if (t >= n) return;
+    const int k = (int)(t % nz);
+    const int j = (int)((t / nz) % ny);
+    const int i = i0 + (int)(t / ((uint64_t)nz * ny));
+    const uint64_t idx = ((uint64_t)i * ny + j) * nz + k;          // global particle index
+    float c[3] = {__fadd_rn(__fmul_rn((float)i, spacing), ox), __fadd_rn(__fmul_rn((float)j, spacing), oy),
+                  __fadd_rn(__fmul_rn((float)k, spacing), oz)};
+    if (jitter > 0.0f) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const uint32_t u = hash32(seed, (uint32_t)(3 * idx + a));
+            const float f = __fmul_rn((float)(u >> 8), 1.0f / 16777216.0f);
+            c[a] = __fadd_rn(c[a], __fmul_rn(__fsub_rn(__fmul_rn(2.0f, f), 1.0f), jitter));
+        }
+    }
+    posid[t] = make_float4(c[0], c[1], c[2], __uint_as_float((uint32_t)idx));
+    velrho[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    keys[t] = cell_key_slab(c[0], c[1], c[2], g, W, R);
+}
+
+// own keys (unsorted, as written by k_integrate_slab) -> leavers into the migration buffers,
+// boundary-layer / NaN counts.  send == nullptr: leavers are only counted (scene distribution).
+__global__ void __launch_bounds__(TPB)
+k_classify(const uint32_t* __restrict__ keys, const float4* __restrict__ posid,
+           const float4* __restrict__ velrho, uint32_t n, GridDev g, int W, int R,
+           Migrant* __restrict__ sendL, Migrant* __restrict__ sendR, uint32_t cap_mig,
+           uint32_t* __restrict__ counts) {
+    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    const uint32_t key = (s < n) ? keys[s] : 0xFFFFFFFFu;
+    const uint32_t plane = (uint32_t)g.dim[1] * (uint32_t)g.dim[2];
+    const bool goneL = key == g.num_cells + 1u, goneR = key == g.num_cells + 2u;
+    const bool isnan = key == g.num_cells;
+    const bool valid = key < g.num_cells;
+    const uint32_t cxl = valid ? key / plane : 0u;
+    const bool inL = valid && cxl < (uint32_t)(2 * R);
+    const bool inR = valid && cxl >= (uint32_t)W;
+    if (goneL || goneR) {
+        const uint32_t slot = atomicAdd(counts + (goneL ? CNT_LEAVE_L : CNT_LEAVE_R), 1u);
+        Migrant* dst = goneL ? sendL : sendR;
+        if (dst) {
+            if (slot < cap_mig) { dst[slot].posid = posid[s]; dst[slot].velrho = velrho[s]; }
+            else counts[CNT_ERR_OVERFLOW] = 1u;
+        }
+    }
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t mL = __ballot_sync(0xffffffffu, inL), mR = __ballot_sync(0xffffffffu, inR);
+    const uint32_t mN = __ballot_sync(0xffffffffu, isnan);
+    if (lane == 0) {
+        if (mL) atomicAdd(counts + CNT_HALO_L, (uint32_t)__popc(mL));
+        if (mR) atomicAdd(counts + CNT_HALO_R, (uint32_t)__popc(mR));
+        if (mN) atomicAdd(counts + CNT_NAN, (uint32_t)__popc(mN));
+    }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_migrant_ids(const Migrant* __restrict__ recv, uint32_t n, uint32_t* __restrict__ ids) {
+    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+    if (t < n) ids[t] = __float_as_uint(recv[t].posid.w);
+}
+
+// immigrants, in ascending particle-id order, behind the own particles; their keys
+__global__ void __launch_bounds__(TPB)
+k_unpack_migrants(const Migrant* __restrict__ recv, const uint32_t* __restrict__ order, uint32_t n,
+                  float4* __restrict__ posid, float4* __restrict__ velrho,
+                  uint32_t* __restrict__ keys, GridDev g, int W, int R, uint32_t* __restrict__ counts) {
+    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+    if (t >= n) return;
+    const Migrant m = recv[order ? order[t] : t];
+    posid[t] = m.posid;
+    velrho[t] = m.velrho;
+    const uint32_t key = cell_key_slab(m.posid.x, m.posid.y, m.posid.z, g, W, R);
+    keys[t] = key;
+    // an immigrant must land in the boundary layer next to the rank it came from
+    if (key >= g.num_cells) counts[CNT_ERR_IMMIGRANT] = 1u;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_gather_slab(const uint32_t* __restrict__ sorted_keys, const uint32_t* __restrict__ perm,
+              const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
+              float4* __restrict__ pos_out, float4* __restrict__ vel_out,
+              uint32_t* __restrict__ skeys, uint32_t n) {
+    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t src = perm[s];
+    pos_out[s] = pos_in[src];
+    vel_out[s] = vel_in[src];
+    skeys[s] = sorted_keys[s];
+}
+
+__global__ void __launch_bounds__(TPB)
+k_ghost_keys(const float4* __restrict__ posid, uint32_t* __restrict__ skeys, uint32_t n, GridDev g) {
+    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+    if (t >= n) return;
+    const float4 p = posid[t];
+    skeys[t] = cell_key(p.x, p.y, p.z, g);
+}
+
+// Lower-bound cell table over the logical concatenation  A = slots [baseA, baseA+lenA)  (ghost L +
+// valid own), B = slots [baseB, baseB+lenB) (ghost R); own particles with NaN positions sit
+// between A and B and are in no cell.  table has table_len entries.
+__global__ void __launch_bounds__(TPB)
+k_cells_slab(const uint32_t* __restrict__ skeys, uint32_t baseA, uint32_t lenA, uint32_t baseB,
+             uint32_t lenB, uint32_t* __restrict__ table, uint32_t table_len,
+             uint4* __restrict__ gap_list, uint32_t* __restrict__ gap_count) {
+    const uint32_t l = blockIdx.x * TPB + threadIdx.x;
+    const uint32_t total = lenA + lenB;
+    if (l > total) return;
+    auto slot_of = [&](uint32_t q) { return q < lenA ? baseA + q : baseB + (q - lenA); };
+    const uint32_t slot = (l < total) ? slot_of(l) : baseB + lenB;
+    const uint32_t key_here = (l < total) ? skeys[slot] : table_len - 1u;
+    const uint32_t lo = (l == 0) ? 0u : skeys[slot_of(l - 1)] + 1u;
+    if (key_here < lo) return;
+    const uint32_t len = key_here - lo + 1u;
+    if (len <= GAP_INLINE) {
+        for (uint32_t c = lo; c <= key_here; c++) table[c] = slot;
+    } else {                                   // long empty run: filled cooperatively (grid.cu)
+        gap_list[atomicAdd(gap_count, 1u)] = make_uint4(lo, len, slot, 0u);
+    }
+}
+
+// integrate_comp.glsl:35-82 on the own slots + next-step slab keys (same arithmetic as k_integrate)
+__device__ __forceinline__ void integrate_axis(float& x, float& v, float f, float rho, float lo,
+                                               float up, const SphDev& sp) {
+    const float a = __fdiv_rn(f, rho);
+    v = __fadd_rn(v, __fmul_rn(sp.dt, a));
+    x = __fadd_rn(x, __fmul_rn(sp.dt, v));
+    if (x < lo)      { x = lo; v = __fmul_rn(v, -sp.damping); }
+    else if (x > up) { x = up; v = __fmul_rn(v, -sp.damping); }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_integrate_slab(float4* __restrict__ posid, float4* __restrict__ velrho,
+                 const float4* __restrict__ forcep, uint32_t* __restrict__ keys, uint32_t n,
+                 GridDev g, SphDev sp, int W, int R) {
+    const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    float4 p = posid[i];
+    float4 v = velrho[i];
+    const float4 f = forcep[i];
+    integrate_axis(p.x, v.x, f.x, v.w, sp.lower[0], sp.upper[0], sp);
+    integrate_axis(p.y, v.y, f.y, v.w, sp.lower[1], sp.upper[1], sp);
+    integrate_axis(p.z, v.z, f.z, v.w, sp.lower[2], sp.upper[2], sp);
+    posid[i] = p;
+    velrho[i] = v;
+    keys[i] = cell_key_slab(p.x, p.y, p.z, g, W, R);
+}
+
+__global__ void __launch_bounds__(TPB)
+k_pack_records(const float4* __restrict__ posid, const float4* __restrict__ velrho,
+               const float4* __restrict__ forcep, uint32_t n, float4* __restrict__ rec,
+               uint32_t* __restrict__ ids) {
+    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    if (s >= n) return;
+    const float4 p = posid[s], v = velrho[s], f = forcep[s];
+    rec[4 * (size_t)s + 0] = make_float4(p.x, p.y, p.z, 1.0f);
+    rec[4 * (size_t)s + 1] = make_float4(v.x, v.y, v.z, 0.0f);
+    rec[4 * (size_t)s + 2] = make_float4(f.x, f.y, f.z, 0.0f);
+    rec[4 * (size_t)s + 3] = make_float4(v.w, f.w, 0.0f, 0.0f);
+    ids[s] = __float_as_uint(p.w);
+}
+
+// ---- neighbour exchange --------------------------------------------------------------------------
+// Sends sendL/sendR to the left/right rank and receives recvL/recvR from them (byte counts; a
+// rank at the end of the chain has no neighbour on that side).  LOCAL transport: the "ranks" are
+// contexts of this process sharing one stream, so a receive is a device copy out of the
+// neighbour's send pointer; the group driver posts all sends before any receive runs.
+struct Posted { const void* toL = nullptr; const void* toR = nullptr; };
+
+int exchange_nccl(nprsph_ctx* c, const void* sendL, size_t nL, const void* sendR, size_t nR,
+                  void* recvL, size_t rL, void* recvR, size_t rR) {
+    DistState* d = c->dist;
+    NcclApi* api = nccl();
+    ncclComm_t comm = (ncclComm_t)d->nccl_comm;
+    NCK(c, api->GroupStart());
+    if (d->rank > 0) {
+        if (nL) NCK(c, api->Send(sendL, nL, ncclChar, d->rank - 1, comm, c->stream));
+        if (rL) NCK(c, api->Recv(recvL, rL, ncclChar, d->rank - 1, comm, c->stream));
+    }
+    if (d->rank + 1 < d->world) {
+        if (nR) NCK(c, api->Send(sendR, nR, ncclChar, d->rank + 1, comm, c->stream));
+        if (rR) NCK(c, api->Recv(recvR, rR, ncclChar, d->rank + 1, comm, c->stream));
+    }
+    NCK(c, api->GroupEnd());
+    return NPRSPH_OK;
+}
+
+struct Xfer { const void* sendL; size_t nL; const void* sendR; size_t nR; void* recvL; size_t rL; void* recvR; size_t rR; };
+
+int exchange_group(nprsph_ctx** cs, int n, const Xfer* x) {
+    if (n == 1 && cs[0]->dist->transport == NPRSPH_TRANSPORT_NCCL)
+        return exchange_nccl(cs[0], x[0].sendL, x[0].nL, x[0].sendR, x[0].nR, x[0].recvL, x[0].rL, x[0].recvR, x[0].rR);
+    for (int r = 0; r < n; r++) {          // LOCAL: rank r receives from r-1 (its sendR) and r+1 (its sendL)
+        nprsph_ctx* c = cs[r];
+        if (r > 0 && x[r].rL) {
+            if (x[r].rL != x[r - 1].nR) return fail(c, NPRSPH_ERR_COMM, "local exchange size mismatch%s");
+            CK(c, cudaMemcpyAsync(x[r].recvL, x[r - 1].sendR, x[r].rL, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (r + 1 < n && x[r].rR) {
+            if (x[r].rR != x[r + 1].nL) return fail(c, NPRSPH_ERR_COMM, "local exchange size mismatch%s");
+            CK(c, cudaMemcpyAsync(x[r].recvR, x[r + 1].sendL, x[r].rR, cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
+    return NPRSPH_OK;
+}
+
+// ---- host-side phases -------------------------------------------------------------------------------
+int setup_local_grid(nprsph_ctx* c) {
+    DistState* d = c->dist;
+    int rc = refresh_params(c);
+    if (rc) return rc;
+    d->R = c->grid.reach;
+    d->lg = c->grid;
+    d->lg.x_off = d->X0 - d->R;
+    d->lg.dimx_global = c->grid.dim[0];
+    d->lg.dim[0] = d->W + 2 * d->R;
+    const uint64_t cells = (uint64_t)d->lg.dim[0] * d->lg.dim[1] * d->lg.dim[2];
+    if (cells + 4 >= (1ull << 32)) return fail(c, NPRSPH_ERR_INVALID, "local grid too large%s");
+    d->lg.num_cells = (uint32_t)cells;
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) <= cells + 2) bits++;     // keys 0..num_cells+2
+    d->key_bits = bits;
+    const size_t need = (size_t)cells + 4;
+    if (need > c->cell_cap) {
+        CK(c, realloc_dev(c->cell_start, need));
+        c->cell_cap = need;
+    }
+    const size_t gaps = gap_list_capacity((uint32_t)cells + 2u, d->cap_total ? d->cap_total : 1);
+    if (gaps > c->gap_cap) {
+        CK(c, realloc_dev(c->gap_list, gaps));
+        c->gap_cap = gaps;
+    }
+    return NPRSPH_OK;
+}
+
+int alloc_slab(nprsph_ctx* c, uint64_t cap_own, uint64_t cap_ghost, uint64_t cap_mig) {
+    DistState* d = c->dist;
+    const uint64_t total = cap_own + 2 * cap_ghost;
+    if (total >= (1ull << 30)) return fail(c, NPRSPH_ERR_INVALID, "slab capacity too large%s");
+    CK(c, cudaStreamSynchronize(c->stream));
+    { float4* a = (float4*)c->aos; CK(c, realloc_dev(a, total * 4)); c->aos = a; }
+    for (int b = 0; b < 2; b++) {
+        CK(c, realloc_dev(c->pos[b], total));
+        CK(c, realloc_dev(c->vel[b], total));
+        CK(c, realloc_dev(c->keys[b], total));
+        CK(c, realloc_dev(c->vals[b], total));
+    }
+    CK(c, realloc_dev(c->frc[0], total));
+    CK(c, realloc_dev(c->frc[1], (size_t)0));
+    { char* w = (char*)c->sort_ws; CK(c, realloc_dev(w, sort_workspace_bytes(total))); c->sort_ws = w; }
+    if (!(c->cfg.flags & NPRSPH_FLAG_NO_HITMASK)) CK(c, realloc_dev(c->hitmask, total * (HIT_WORDS + 1)));
+    if (c->cfg.flags & NPRSPH_FLAG_COUNT_NEIGHBOURS) {
+        CK(c, realloc_dev(c->counts_rho, total));
+        CK(c, realloc_dev(c->counts_force, total));
+    }
+    CK(c, realloc_dev(d->skeys, total));
+    CK(c, realloc_dev(d->sendL, cap_mig));
+    CK(c, realloc_dev(d->sendR, cap_mig));
+    CK(c, realloc_dev(d->recv, 2 * cap_mig));
+    CK(c, realloc_dev(d->mig_ids, 8 * cap_mig));
+    { char* w = (char*)d->mig_sort_ws; CK(c, realloc_dev(w, sort_workspace_bytes(2 * cap_mig))); d->mig_sort_ws = w; }
+    c->cap = total;
+    c->n = 0;
+    d->cap_own = (uint32_t)cap_own; d->cap_ghost = (uint32_t)cap_ghost; d->cap_mig = (uint32_t)cap_mig;
+    d->cap_total = (uint32_t)total; d->own_off = (uint32_t)cap_ghost;
+    return NPRSPH_OK;
+}
+
+// Everything between "positions + unsorted slab keys of the own particles are final" and "cell
+// table and ghosts are ready for k_rho", for all local ranks in lock step.
+int prepare_group(nprsph_ctx** cs, int n) {
+    Xfer x[64];
+    // (1) classify + counter exchange, one host sync
+    for (int r = 0; r < n; r++) {
+        nprsph_ctx* c = cs[r]; DistState* d = c->dist;
+        CK(c, cudaSetDevice(c->cfg.device));
+        CK(c, cudaMemsetAsync(d->d_counts, 0, 3 * CNT_WORDS * sizeof(uint32_t), c->stream));
+        if (d->n_own)
+            k_classify<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
+                c->keys[0], c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, d->n_own, d->lg,
+                d->W, d->R, d->first_prepare ? nullptr : d->sendL, d->first_prepare ? nullptr : d->sendR,
+                d->cap_mig, d->d_counts);
+        x[r] = {d->d_counts, CNT_WORDS * 4, d->d_counts, CNT_WORDS * 4,
+                d->d_counts + CNT_WORDS, CNT_WORDS * 4, d->d_counts + 2 * CNT_WORDS, CNT_WORDS * 4};
+    }
+    int rc = exchange_group(cs, n, x);
+    if (rc) return rc;
+    for (int r = 0; r < n; r++) {
+        nprsph_ctx* c = cs[r];
+        CK(c, cudaMemcpyAsync(c->dist->h_counts, c->dist->d_counts, 3 * CNT_WORDS * sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, c->stream));
+    }
+    for (int r = 0; r < n; r++) CK(cs[r], cudaStreamSynchronize(cs[r]->stream));
+
+    // (2) sizes, migrant exchange
+    uint32_t inL[64], inR[64], leaveL[64], leaveR[64], dropped[64];
+    for (int r = 0; r < n; r++) {
+        nprsph_ctx* c = cs[r]; DistState* d = c->dist;
+        const uint32_t* mine = d->h_counts;
+        const uint32_t* fromL = d->h_counts + CNT_WORDS;
+        const uint32_t* fromR = d->h_counts + 2 * CNT_WORDS;
+        const bool hasL = d->rank > 0, hasR = d->rank + 1 < d->world;
+        if (mine[CNT_ERR_OVERFLOW]) return fail(c, NPRSPH_ERR_NOMEM, "migration buffer overflow (raise max_migrate)%s");
+        dropped[r] = mine[CNT_LEAVE_L] + mine[CNT_LEAVE_R];
+        const bool fp = d->first_prepare;
+        leaveL[r] = fp ? 0u : mine[CNT_LEAVE_L];
+        leaveR[r] = fp ? 0u : mine[CNT_LEAVE_R];
+        if (!fp && ((!hasL && leaveL[r]) || (!hasR && leaveR[r])))
+            return fail(c, NPRSPH_ERR_STATE, "particle left the global grid through a slab face%s");
+        inL[r] = (hasL && !fp) ? fromL[CNT_LEAVE_R] : 0u;
+        inR[r] = (hasR && !fp) ? fromR[CNT_LEAVE_L] : 0u;
+        if (inL[r] + inR[r] > 2 * d->cap_mig || d->n_own + inL[r] + inR[r] > d->cap_own)
+            return fail(c, NPRSPH_ERR_NOMEM, "own-particle capacity exceeded (raise max_own)%s");
+        d->n_nan = mine[CNT_NAN];
+        // boundary layers after migration: stayers + the immigrants that arrive through that face
+        d->hL = mine[CNT_HALO_L] + inL[r];
+        d->hR = mine[CNT_HALO_R] + inR[r];
+        d->gL = hasL ? fromL[CNT_HALO_R] + leaveL[r] : 0u;
+        d->gR = hasR ? fromR[CNT_HALO_L] + leaveR[r] : 0u;
+        if (d->gL > d->cap_ghost || d->gR > d->cap_ghost)
+            return fail(c, NPRSPH_ERR_NOMEM, "ghost capacity exceeded (raise max_ghost)%s");
+        d->migrated_total += leaveL[r] + leaveR[r];
+        x[r] = {d->sendL, leaveL[r] * sizeof(Migrant), d->sendR, leaveR[r] * sizeof(Migrant),
+                d->recv, inL[r] * sizeof(Migrant), d->recv + inL[r], inR[r] * sizeof(Migrant)};
+    }
+    rc = exchange_group(cs, n, x);
+    if (rc) return rc;
+
+    // (3) immigrants behind the own particles (ascending id), sort, gather into [own_off, ...)
+    for (int r = 0; r < n; r++) {
+        nprsph_ctx* c = cs[r]; DistState* d = c->dist;
+        CK(c, cudaSetDevice(c->cfg.device));
+        const uint32_t n_in = inL[r] + inR[r];
+        const uint32_t n_pre = d->n_own + n_in;
+        float4* pos = c->pos[c->cur] + d->own_off;
+        float4* vel = c->vel[c->cur] + d->own_off;
+        if (n_in) {
+            uint32_t* ids = d->mig_ids;
+            uint32_t* order = nullptr;
+            if (n_in > 1) {
+                k_migrant_ids<<<blocks_for(n_in), TPB, 0, c->stream>>>(d->recv, n_in, ids);
+                bool in_b = false;
+                CK(c, sort_pairs(ids, ids + 2 * d->cap_mig, ids + 4 * d->cap_mig, ids + 6 * d->cap_mig, n_in,
+                                 32, true, d->mig_sort_ws, c->num_sms, c->stream, &in_b));
+                order = in_b ? ids + 6 * d->cap_mig : ids + 2 * d->cap_mig;
+            }
+            k_unpack_migrants<<<blocks_for(n_in), TPB, 0, c->stream>>>(
+                d->recv, order, n_in, pos + d->n_own, vel + d->n_own, c->keys[0] + d->n_own, d->lg, d->W,
+                d->R, d->d_counts);
+        }
+        const uint32_t n_new = n_pre - (d->first_prepare ? dropped[r] : leaveL[r] + leaveR[r]);
+        bool in_b = false;
+        CK(c, sort_pairs(c->keys[0], c->vals[0], c->keys[1], c->vals[1], n_pre, d->key_bits, true,
+                         c->sort_ws, c->num_sms, c->stream, &in_b));
+        const int nxt = 1 - c->cur;
+        if (n_new)
+            k_gather_slab<<<blocks_for(n_new), TPB, 0, c->stream>>>(
+                in_b ? c->keys[1] : c->keys[0], in_b ? c->vals[1] : c->vals[0], pos, vel,
+                c->pos[nxt] + d->own_off, c->vel[nxt] + d->own_off, d->skeys + d->own_off, n_new);
+        c->cur = nxt;
+        d->n_own = n_new;
+        d->first_prepare = false;
+        // (4) boundary-layer positions -> neighbours' ghost slots
+        float4* p = c->pos[c->cur];
+        const uint32_t right0 = d->own_off + d->n_own - d->n_nan - d->hR;
+        x[r] = {p + d->own_off, (d->rank > 0 ? d->hL : 0u) * sizeof(float4),
+                p + right0, (d->rank + 1 < d->world ? d->hR : 0u) * sizeof(float4),
+                p + d->own_off - d->gL, d->gL * sizeof(float4),
+                p + d->own_off + d->n_own, d->gR * sizeof(float4)};
+    }
+    rc = exchange_group(cs, n, x);
+    if (rc) return rc;
+
+    // (5) ghost keys + cell table over [ghost L | own | ghost R]
+    for (int r = 0; r < n; r++) {
+        nprsph_ctx* c = cs[r]; DistState* d = c->dist;
+        CK(c, cudaSetDevice(c->cfg.device));
+        float4* p = c->pos[c->cur];
+        if (d->gL) k_ghost_keys<<<blocks_for(d->gL), TPB, 0, c->stream>>>(p + d->own_off - d->gL, d->skeys + d->own_off - d->gL, d->gL, d->lg);
+        if (d->gR) k_ghost_keys<<<blocks_for(d->gR), TPB, 0, c->stream>>>(p + d->own_off + d->n_own, d->skeys + d->own_off + d->n_own, d->gR, d->lg);
+        const uint32_t lenA = d->gL + d->n_own - d->n_nan, lenB = d->gR;
+        CK(c, cudaMemsetAsync(c->gap_count, 0, sizeof(uint32_t), c->stream));
+        k_cells_slab<<<blocks_for((uint64_t)lenA + lenB + 1), TPB, 0, c->stream>>>(
+            d->skeys, d->own_off - d->gL, lenA, d->own_off + d->n_own, lenB, c->cell_start,
+            d->lg.num_cells + 4u, c->gap_list, c->gap_count);
+        launch_fill_gaps(c->gap_list, c->gap_count, c->cell_start, c->num_sms, c->stream);
+        CK(c, cudaGetLastError());
+    }
+    return NPRSPH_OK;
+}
+
+int ensure_prepared(nprsph_ctx** cs, int n) {
+    bool all = true;
+    for (int r = 0; r < n; r++) all = all && cs[r]->dist->prepared;
+    if (all) return NPRSPH_OK;
+    int rc = prepare_group(cs, n);
+    if (rc) return rc;
+    for (int r = 0; r < n; r++) cs[r]->dist->prepared = true;
+    return NPRSPH_OK;
+}
+
+int step_group(nprsph_ctx** cs, int n) {
+    Xfer x[64];
+    int rc = ensure_prepared(cs, n);
+    if (rc) return rc;
+    for (int r = 0; r < n; r++) {
+        nprsph_ctx* c = cs[r]; DistState* d = c->dist;
+        CK(c, cudaSetDevice(c->cfg.device));
+        launch_rho(c->pos[c->cur], c->vel[c->cur], nullptr, c->cell_start, d->own_off, d->n_own, d->lg,
+                   c->sph, nullptr, c->hitmask, d->cap_total, c->stream);
+        float4* v = c->vel[c->cur];
+        const uint32_t right0 = d->own_off + d->n_own - d->n_nan - d->hR;
+        x[r] = {v + d->own_off, (d->rank > 0 ? d->hL : 0u) * sizeof(float4),
+                v + right0, (d->rank + 1 < d->world ? d->hR : 0u) * sizeof(float4),
+                v + d->own_off - d->gL, d->gL * sizeof(float4),
+                v + d->own_off + d->n_own, d->gR * sizeof(float4)};
+    }
+    rc = exchange_group(cs, n, x);                 // (velocity, rho) of the boundary layers
+    if (rc) return rc;
+    for (int r = 0; r < n; r++) {
+        nprsph_ctx* c = cs[r]; DistState* d = c->dist;
+        CK(c, cudaSetDevice(c->cfg.device));
+        launch_force(c->pos[c->cur], c->vel[c->cur], c->frc[0], c->cell_start, d->own_off, d->n_own,
+                     d->lg, c->sph, nullptr, c->hitmask, d->cap_total, c->stream);
+        if (d->n_own)
+            k_integrate_slab<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
+                c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off,
+                c->keys[0], d->n_own, d->lg, c->sph, d->W, d->R);
+        CK(c, cudaGetLastError());
+        d->prepared = false;                        // positions moved: keys/ghosts/table are stale
+        d->steps_done++;
+        c->steps_done++;
+    }
+    return NPRSPH_OK;
+}
+
+int check_group(nprsph_ctx** cs, int n) {
+    if (!cs || n < 1 || n > 64) return NPRSPH_ERR_INVALID;
+    for (int r = 0; r < n; r++) {
+        if (!cs[r]) return NPRSPH_ERR_INVALID;
+        if (cs[r]->sticky) return cs[r]->sticky;
+        if (!cs[r]->dist) return fail(cs[r], NPRSPH_ERR_STATE, "nprsph_dist_init() was not called%s");
+        if (n > 1 && (cs[r]->dist->transport != NPRSPH_TRANSPORT_LOCAL || cs[r]->dist->rank != r ||
+                      cs[r]->dist->world != n || cs[r]->stream != cs[0]->stream))
+            return fail(cs[r], NPRSPH_ERR_INVALID,
+                        "several contexts in one call need the LOCAL transport, ranks 0..n-1 and one shared stream%s");
+    }
+    return NPRSPH_OK;
+}
+
+}  // namespace
+
+void nprsph::dist_destroy(nprsph_ctx* c) {
+    DistState* d = c->dist;
+    if (!d) return;
+    if (d->nccl_comm && nccl() && nccl()->CommDestroy) nccl()->CommDestroy((ncclComm_t)d->nccl_comm);
+    cudaFree(d->sendL); cudaFree(d->sendR); cudaFree(d->recv); cudaFree(d->skeys);
+    cudaFree(d->d_counts); cudaFree(d->mig_ids); cudaFree(d->mig_sort_ws);
+    if (d->h_counts) cudaFreeHost(d->h_counts);
+    delete d;
+    c->dist = nullptr;
+}
+
+// ================================ C ABI ==========================================================
+extern "C" {
+
+int nprsph_slab_partition(const uint64_t* hist, int dimx, int world, int min_width, int32_t* bounds) {
+    if (!hist || !bounds || dimx < 1 || world < 1 || min_width < 1 || (int64_t)world * min_width > dimx)
+        return NPRSPH_ERR_INVALID;
+    uint64_t total = 0;
+    for (int x = 0; x < dimx; x++) total += hist[x];
+    bounds[0] = 0;
+    bounds[world] = dimx;
+    uint64_t acc = 0;
+    int x = 0;
+    for (int r = 1; r < world; r++) {
+        // smallest boundary whose prefix reaches r/world of the particles, leaving every slab
+        // (also the remaining ones) at least min_width cells
+        const uint64_t target = (total * (uint64_t)r + (uint64_t)world - 1) / (uint64_t)world;
+        const int lo = bounds[r - 1] + min_width, hi = dimx - (world - r) * min_width;
+        while (x < hi && (acc < target || x < lo)) acc += hist[x++];
+        while (x > hi) acc -= hist[--x];
+        bounds[r] = x;
+    }
+    return NPRSPH_OK;
+}
+
+int nprsph_dist_unique_id(uint8_t id[128]) {
+    if (!id) return NPRSPH_ERR_INVALID;
+    NcclApi* api = nccl();
+    if (!api) return NPRSPH_ERR_UNSUPPORTED;
+    ncclUniqueId u;
+    if (api->GetUniqueId(&u) != ncclSuccess) return NPRSPH_ERR_COMM;
+    static_assert(sizeof u == 128, "ncclUniqueId size");
+    memcpy(id, &u, 128);
+    return NPRSPH_OK;
+}
+
+int nprsph_dist_init(nprsph_ctx* c, const nprsph_dist_config* cfg) {
+    GUARD(c);
+    if (!cfg || cfg->struct_size != sizeof(nprsph_dist_config) || cfg->world < 1 || cfg->rank < 0 ||
+        cfg->rank >= cfg->world)
+        return fail(c, NPRSPH_ERR_INVALID, "bad nprsph_dist_config%s");
+    if (c->dist) return fail(c, NPRSPH_ERR_STATE, "nprsph_dist_init() called twice%s");
+    DistState* d = new (std::nothrow) DistState();
+    if (!d) return fail(c, NPRSPH_ERR_NOMEM, "out of host memory%s");
+    d->rank = cfg->rank; d->world = cfg->world; d->transport = cfg->transport;
+    c->dist = d;
+    CK(c, cudaMalloc(&d->d_counts, 3 * CNT_WORDS * sizeof(uint32_t)));
+    CK(c, cudaMallocHost(&d->h_counts, 3 * CNT_WORDS * sizeof(uint32_t)));
+    if (cfg->transport == NPRSPH_TRANSPORT_NCCL && cfg->world > 1) {
+        NcclApi* api = nccl();
+        if (!api) return fail(c, NPRSPH_ERR_UNSUPPORTED, "libnccl.so.2 not found%s");
+        ncclUniqueId u;
+        memcpy(&u, cfg->nccl_id, 128);
+        ncclComm_t comm;
+        NCK(c, api->CommInitRank(&comm, cfg->world, u, cfg->rank));
+        d->nccl_comm = comm;
+    } else if (cfg->transport != NPRSPH_TRANSPORT_NCCL && cfg->transport != NPRSPH_TRANSPORT_LOCAL) {
+        return fail(c, NPRSPH_ERR_INVALID, "unknown transport%s");
+    }
+    // capacities requested by the caller (0 = derived from the scene)
+    d->cap_own = (uint32_t)cfg->max_own; d->cap_ghost = (uint32_t)cfg->max_ghost; d->cap_mig = (uint32_t)cfg->max_migrate;
+    // the single-GPU particle buffer of create() is not used in slab mode
+    c->n = 0;
+    return NPRSPH_OK;
+}
+
+int nprsph_dist_scene_block(nprsph_ctx* c, int nx, int ny, int nz, float spacing, const float origin[3],
+                            float jitter, uint32_t seed) {
+    GUARD(c);
+    DistState* d = c->dist;
+    if (!d) return fail(c, NPRSPH_ERR_STATE, "nprsph_dist_init() was not called%s");
+    if (nx < 1 || ny < 1 || nz < 1 || !(spacing > 0.0f) || (uint64_t)nx * ny * nz >= (1ull << 32))
+        return fail(c, NPRSPH_ERR_INVALID, "bad block%s");
+    int rc = refresh_params(c);
+    if (rc) return rc;
+    const float o[3] = {origin ? origin[0] : 0.f, origin ? origin[1] : 0.f, origin ? origin[2] : 0.f};
+    // every rank derives the same count-balanced slab boundaries from the lattice planes
+    const GridDev& g = c->grid;
+    const int R = g.reach;
+    std::string herr;
+    uint64_t* hist = new (std::nothrow) uint64_t[g.dim[0]]();
+    int32_t* bounds = new (std::nothrow) int32_t[d->world + 1];
+    if (!hist || !bounds) { delete[] hist; delete[] bounds; return fail(c, NPRSPH_ERR_NOMEM, "out of host memory%s"); }
+    auto plane_cell = [&](int i) {
+        float u = ((float)i * spacing + o[0] - g.lo[0]) * g.inv_cell;
+        if (!(u >= 0.0f)) u = 0.0f;
+        if (u > (float)(g.dim[0] - 1)) u = (float)(g.dim[0] - 1);
+        return (int)u;
+    };
+    for (int i = 0; i < nx; i++) hist[plane_cell(i)] += (uint64_t)ny * nz;
+    rc = nprsph_slab_partition(hist, g.dim[0], d->world, 2 * R, bounds);
+    if (rc) { delete[] hist; delete[] bounds; return fail(c, NPRSPH_ERR_INVALID, "grid too narrow for this many ranks (each slab needs 2*reach cells)%s"); }
+    d->X0 = bounds[d->rank]; d->X1 = bounds[d->rank + 1]; d->W = d->X1 - d->X0;
+    // candidate lattice planes: those whose cell (ignoring jitter) is within one cell of the slab
+    int i0 = nx, i1 = 0;
+    for (int i = 0; i < nx; i++) {
+        const int cx = plane_cell(i);
+        if (cx >= d->X0 - 1 && cx <= d->X1) { if (i < i0) i0 = i; if (i + 1 > i1) i1 = i + 1; }
+    }
+    uint64_t own_est = 0;
+    for (int x = d->X0; x < d->X1; x++) own_est += hist[x];
+    delete[] hist; delete[] bounds;
+    const int ni = i1 > i0 ? i1 - i0 : 0;
+    const uint64_t n_cand = (uint64_t)ni * ny * nz;
+    const uint64_t n_global = (uint64_t)nx * ny * nz;
+    // capacities: own = 1.5x the fair share (the static slabs let fluid pile up downstream),
+    // ghosts = the particles of `reach`+2 cell layers of the block's cross-section, twice over
+    const double layers = (double)(R + 2) / ((double)spacing * g.inv_cell) + 2.0;
+    uint64_t cap_ghost = d->cap_ghost ? d->cap_ghost : (uint64_t)(2.0 * layers * ny * nz) + 4096;
+    uint64_t cap_own = d->cap_own ? d->cap_own : (uint64_t)(1.5 * (double)n_global / d->world) + 65536;
+    if (cap_own < n_cand) cap_own = n_cand;
+    if (cap_own < own_est) cap_own = own_est;
+    uint64_t cap_mig = d->cap_mig ? d->cap_mig : cap_ghost / 2 + 1024;
+    rc = alloc_slab(c, cap_own, cap_ghost, cap_mig);
+    if (rc) return rc;
+    rc = setup_local_grid(c);
+    if (rc) return rc;
+    c->cur = 0;
+    if (n_cand)
+        k_slab_scene<<<blocks_for(n_cand), TPB, 0, c->stream>>>(
+            c->pos[0] + d->own_off, c->vel[0] + d->own_off, c->keys[0], i0, ni, ny, nz, spacing, o[0],
+            o[1], o[2], jitter, seed, d->lg, d->W, d->R);
+    CK(c, cudaGetLastError());
+    d->n_own = (uint32_t)n_cand;
+    d->first_prepare = true;
+    d->prepared = false;
+    d->ready = true;
+    d->steps_done = 0;
+    d->migrated_total = 0;
+    return NPRSPH_OK;
+}
+
+int nprsph_dist_link_local(nprsph_ctx** ranks, int n) {
+    if (!ranks || n < 1) return NPRSPH_ERR_INVALID;
+    for (int r = 0; r < n; r++) {
+        if (!ranks[r] || !ranks[r]->dist) return NPRSPH_ERR_STATE;
+        ranks[r]->dist->left = r > 0 ? ranks[r - 1] : nullptr;
+        ranks[r]->dist->right = r + 1 < n ? ranks[r + 1] : nullptr;
+    }
+    return check_group(ranks, n);
+}
+
+int nprsph_dist_step(nprsph_ctx** ranks, int n_local, int steps) {
+    int rc = check_group(ranks, n_local);
+    if (rc) return rc;
+    if (steps < 0) return NPRSPH_ERR_INVALID;
+    for (int r = 0; r < n_local; r++) {
+        if (!ranks[r]->dist->ready) return fail(ranks[r], NPRSPH_ERR_STATE, "no scene distributed yet%s");
+ 
+        const bool dirty = ranks[r]->params_dirty;
+        rc = refresh_params(ranks[r]);
+        if (rc) return rc;
+        if (dirty) {                                 // constants may change freely; the grid may not
+            const GridDev old = ranks[r]->dist->lg;
+            rc = setup_local_grid(ranks[r]);
+            if (rc) return rc;
+            if (memcmp(&old, &ranks[r]->dist->lg, sizeof old) != 0)
+                return fail(ranks[r], NPRSPH_ERR_UNSUPPORTED,
+                            "changing the smoothing length or the box after the scene was distributed is not supported%s");
+        }
+    }
+    if (ranks[0]->paused) return NPRSPH_OK;                  // if (simulate) ..., Main.cpp:293
+    for (int s = 0; s < steps; s++) {
+        rc = step_group(ranks, n_local);
+        if (rc) return rc;
+    }
+    return NPRSPH_OK;
+}
+
+int nprsph_dist_download(nprsph_ctx** ranks, int n_local, int which, nprsph_particle* records,
+                         uint32_t* ids, uint64_t capacity, uint64_t* n_out) {
+    int rc = check_group(ranks, n_local);
+    if (rc) return rc;
+    if (which < 0 || which >= n_local || !n_out) return NPRSPH_ERR_INVALID;
+    // ownership must be current (migration of the last integrate applied): collective prepare
+    rc = ensure_prepared(ranks, n_local);
+    if (rc) return rc;
+    nprsph_ctx* c = ranks[which]; DistState* d = c->dist;
+    CK(c, cudaSetDevice(c->cfg.device));
+    *n_out = d->n_own;
+    if (!records && !ids) return NPRSPH_OK;
+    if (capacity < d->n_own || !records || !ids) return fail(c, NPRSPH_ERR_INVALID, "download buffers too small%s");
+    if (d->n_own) {
+        uint32_t* d_ids = c->vals[1];
+        k_pack_records<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
+            c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off, d->n_own,
+            (float4*)c->aos, d_ids);
+        CK(c, cudaMemcpyAsync(records, c->aos, (size_t)d->n_own * 64, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(ids, d_ids, (size_t)d->n_own * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return NPRSPH_OK;
+}
+
+int nprsph_dist_get_info(nprsph_ctx* c, nprsph_dist_info* out) {
+    GUARD(c);
+    if (!out || !c->dist) return NPRSPH_ERR_INVALID;
+    DistState* d = c->dist;
+    memset(out, 0, sizeof *out);
+    out->rank = d->rank; out->world = d->world;
+    out->x_begin = d->X0; out->x_end = d->X1;
+    out->num_own = d->n_own; out->ghosts_left = d->gL; out->ghosts_right = d->gR;
+    out->migrated_total = d->migrated_total; out->steps_done = d->steps_done;
+    out->cap_own = d->cap_own; out->cap_ghost = d->cap_ghost;
+    out->nan_particles = d->n_nan;
+    return NPRSPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// dist.cuh -- state of the slab-decomposed (multi-GPU) step, one context per GPU / process.
+#pragma once
+
+#include "context.cuh"
+
+namespace nprsph {
+
+struct Migrant { float4 posid, velrho; };      // one particle changing rank (32 B)
+
+enum { CNT_LEAVE_L = 0, CNT_LEAVE_R, CNT_HALO_L, CNT_HALO_R, CNT_NAN, CNT_RESERVED, CNT_ERR_IMMIGRANT,
+       CNT_ERR_OVERFLOW, CNT_WORDS };
+
+struct DistState {
+    int rank = 0, world = 1;
+    int transport = 0;                 // NPRSPH_TRANSPORT_*
+    void* nccl_comm = nullptr;
+    nprsph_ctx* left = nullptr;        // local transport only
+    nprsph_ctx* right = nullptr;
+
+    // slab geometry (global x cell indices) and the local grid derived from ctx->grid
+    int X0 = 0, X1 = 0, W = 0, R = 1;
+    GridDev lg;
+    int key_bits = 1;
+    bool ready = false;                // scene distributed
+    bool prepared = false;             // ownership, ghosts and cell table match the current positions
+
+    // slot layout: [ghost L | own | ghost R]; own particles start at slot own_off
+    uint32_t cap_ghost = 0, cap_own = 0, cap_mig = 0, cap_total = 0, own_off = 0;
+    uint32_t n_own = 0, n_nan = 0, gL = 0, gR = 0, hL = 0, hR = 0;
+    bool first_prepare = true;         // candidates that belong to other ranks are dropped, not sent
+    uint64_t migrated_total = 0, steps_done = 0;
+
+    Migrant *sendL = nullptr, *sendR = nullptr, *recv = nullptr;
+    uint32_t* skeys = nullptr;         // sorted key of every slot
+    uint32_t* d_counts = nullptr;      // [3][CNT_WORDS]: mine, from left, from right
+    uint32_t* h_counts = nullptr;      // pinned mirror
+    uint32_t* mig_ids = nullptr;       // [4][2*cap_mig] scratch: ids, iota, sorted ids, order
+    void* mig_sort_ws = nullptr;
+};
+
+}  // namespace nprsph

@@ -11,7 +11,6 @@ namespace nprsph {
 namespace {
 
 constexpr int TPB = 256;
-constexpr uint32_t GAP_INLINE = 64;   // longer empty-cell runs go to the cooperative fill list
 
 inline unsigned blocks_for(uint64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
@@ -154,6 +153,11 @@ void launch_reorder_cells(const uint32_t* sorted_keys, const uint32_t* perm, con
     else
         k_reorder_cells<false><<<blocks, TPB, 0, st>>>(sorted_keys, perm, pos_in, vel_in, force_in,
             pos_out, vel_out, force_out, cell_start, num_cells, n, gap_list, gap_count);
+    k_fill_gaps<<<num_sms * 4, TPB, 0, st>>>(gap_list, gap_count, cell_start);
+}
+
+void launch_fill_gaps(const uint4* gap_list, const uint32_t* gap_count, uint32_t* cell_start,
+                      int num_sms, cudaStream_t st) {
     k_fill_gaps<<<num_sms * 4, TPB, 0, st>>>(gap_list, gap_count, cell_start);
 }
 

@@ -4,6 +4,9 @@
 
 namespace nprsph {
 
+// longer empty-cell runs of the cell table go to the cooperative fill list (k_fill_gaps)
+constexpr uint32_t GAP_INLINE = 64;
+
 // grid.cu
 void launch_import(const void* aos, float4* posid, float4* velrho, float4* forcep, uint32_t n,
                    cudaStream_t st);
@@ -16,16 +19,18 @@ void launch_reorder_cells(const uint32_t* sorted_keys, const uint32_t* perm, con
                           float4* vel_out, float4* force_out, uint32_t* cell_start,
                           uint32_t num_cells, uint32_t n, uint4* gap_list, uint32_t* gap_count,
                           bool with_force, int num_sms, cudaStream_t st);
+void launch_fill_gaps(const uint4* gap_list, const uint32_t* gap_count, uint32_t* cell_start,
+                      int num_sms, cudaStream_t st);
 void launch_count_nan(const float4* posid, uint32_t n, unsigned long long* out, cudaStream_t st);
 void launch_slot_ids(const float4* posid, uint32_t* ids, uint32_t n, cudaStream_t st);
 
 // sph_passes.cu
 void launch_rho(const float4* posid, float4* velrho, float4* forcep_or_null,
-                const uint32_t* cell_start, uint32_t n, const GridDev& g, const SphDev& sp,
+                const uint32_t* cell_start, uint32_t first, uint32_t n, const GridDev& g, const SphDev& sp,
                 uint32_t* counts_by_id, uint32_t* hitmask_or_null, uint32_t mask_stride,
                 cudaStream_t st);
 void launch_force(const float4* posid, const float4* velrho, float4* forcep,
-                  const uint32_t* cell_start, uint32_t n, const GridDev& g, const SphDev& sp,
+                  const uint32_t* cell_start, uint32_t first, uint32_t n, const GridDev& g, const SphDev& sp,
                   uint32_t* counts_by_id, const uint32_t* hitmask_or_null, uint32_t mask_stride,
                   cudaStream_t st);
 void launch_integrate(float4* posid, float4* velrho, const float4* forcep, uint32_t* keys,

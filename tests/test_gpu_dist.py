@@ -1,0 +1,90 @@
+"""Slab decomposition on ONE GPU through the LOCAL transport: the same protocol
+as the NCCL path -- ownership by global x cell, migration, ghost layers, two halo exchanges per
+step -- must reproduce the single-context run: identical neighbour sets mean the only admissible
+difference is the summation order inside a cell (ghost vs own slot order), i.e. none at all,
+because the slab arrangement is the global cell order restricted to the slab."""
+import numpy as np
+import pytest
+
+from conftest import assert_field_close
+
+pytestmark = pytest.mark.gpu
+
+POS, VEL, FRC, RHO = slice(0, 3), slice(4, 7), slice(8, 11), 12
+
+
+def _scene(oracle, nx, ny, nz, gy=-9.80665):
+    p = oracle.dam_break_params(nx, ny, nz)
+    p.gravity[1] = gy
+    return p
+
+
+@pytest.mark.parametrize("world,cell_subdiv", [(2, 1), (3, 2), (4, 2)])
+def test_slabs_match_single_context(sph, oracle, world, cell_subdiv):
+    from nprsph_b200.dist import SlabGroup
+    nx, ny, nz = 40, 16, 12
+    p = _scene(oracle, nx, ny, nz)
+    ref = sph.Simulation(cell_subdiv=cell_subdiv)
+    ref.apply_params(p)
+    ref.scene_block(nx, ny, nz, 0.005, None, 2e-4, 7)
+    ref.set_paused(False)
+    grp = SlabGroup.local(world, cell_subdiv=cell_subdiv)
+    grp.apply_params(p)
+    grp.scene_block(nx, ny, nz, 0.005, None, 2e-4, 7)
+    grp.set_paused(False)
+    n = nx * ny * nz
+    G0 = grp.gather(n)
+    assert np.array_equal(G0[:, POS], ref.download()[:, POS]), "slab scene == global scene"
+    owned = [grp.info(w).num_own for w in range(world)]
+    assert sum(owned) == n and min(owned) > 0.5 * n / world, owned
+    for chunk in range(6):
+        ref.step(10)
+        grp.step(10)
+        A, G = ref.download(), grp.gather(n)
+        assert not np.isnan(G[:, POS]).any(), "every particle is owned by exactly one rank"
+        for name, cols in (("pos", POS), ("vel", VEL), ("force", FRC), ("rho", RHO)):
+            assert_field_close(G[:, cols], A[:, cols], f"{name}@{10 * (chunk + 1)}", elementwise=False)
+    assert sum(grp.info(w).num_own for w in range(world)) == n
+    grp.close()
+
+
+def test_migration_and_ghosts_under_strong_flow(sph, oracle):
+    """A strong horizontal body force drives many particles through the slab faces."""
+    from nprsph_b200.dist import SlabGroup
+    nx, ny, nz = 36, 12, 10
+    p = _scene(oracle, nx, ny, nz, gy=-2.0)
+    p.gravity[0] = 300.0
+    ref = sph.Simulation(cell_subdiv=2)
+    ref.apply_params(p)
+    ref.scene_block(nx, ny, nz, 0.005, None, 3e-4, 11)
+    ref.set_paused(False)
+    grp = SlabGroup.local(3, cell_subdiv=2)
+    grp.apply_params(p)
+    grp.scene_block(nx, ny, nz, 0.005, None, 3e-4, 11)
+    grp.set_paused(False)
+    n = nx * ny * nz
+    for chunk in range(8):
+        ref.step(15)
+        grp.step(15)
+        A, G = ref.download(), grp.gather(n)
+        assert not np.isnan(G[:, POS]).any()
+        assert_field_close(G[:, POS], A[:, POS], f"pos@{15 * (chunk + 1)}", elementwise=False)
+        assert_field_close(G[:, RHO], A[:, RHO], f"rho@{15 * (chunk + 1)}", elementwise=False)
+    moved = sum(grp.info(w).migrated_total for w in range(3))
+    assert moved > 100, f"scene too static to exercise migration ({moved})"
+    assert all(grp.info(w).ghosts_left + grp.info(w).ghosts_right > 0 for w in range(3))
+    print(f"\n[dist] {moved} particle hand-overs between 3 slabs in 120 steps")
+    grp.close()
+
+
+def test_world_of_one_is_the_plain_step(sph, oracle):
+    from nprsph_b200.dist import SlabGroup
+    p = _scene(oracle, 10, 10, 10)
+    ref = sph.Simulation(cell_subdiv=2)
+    ref.apply_params(p); ref.scene_block(10, 10, 10, 0.005, None, 1e-4, 3); ref.set_paused(False)
+    grp = SlabGroup.local(1, cell_subdiv=2)
+    grp.apply_params(p); grp.scene_block(10, 10, 10, 0.005, None, 1e-4, 3); grp.set_paused(False)
+    ref.step(20); grp.step(20)
+    A, G = ref.download(), grp.gather(1000)
+    assert np.array_equal(G[:, POS], A[:, POS]) and np.array_equal(G[:, RHO], A[:, RHO])
+    grp.close()
