@@ -122,6 +122,100 @@ def relaunch_under_torchrun(args):
 
 
 # ------------------------------------------------------------------------------------------------
+class SingleRunner:
+    """N = 1: one context, the plain C-ABI calls (nprsph_step / upload / download)."""
+
+    def __init__(self, sph, O, args, local, stream):
+        side = args.side
+        self.n_own = side ** 3
+        self.p = O.dam_break_params(side, side, side)
+        self.sim = sph.Simulation(device=local, stream=stream.cuda_stream, cell_subdiv=args.subdiv)
+        self.sim.apply_params(self.p)
+        self.sim.scene_block(side, side, side, 0.005, None, 1e-4 * 0.005, 1234)
+        self.sim.set_paused(False)
+        st = self.sim.stats()
+        self.grid_cells, self.sort_passes = st.num_cells, st.sort_passes
+        # hist + P onesweep + reorder + fill + rho + force + integrate
+        self.launches_per_step = 6 + st.sort_passes
+        self.parallelism = "1 process, 1 GPU"
+        self.api = "nprsph_upload_particles + nprsph_step(1) + nprsph_download_particles, pinned host buffers"
+
+    def step(self, k):
+        self.sim.step(k)
+
+    def profile(self, k):
+        return self.sim.profile_step(k)
+
+    def alloc_host(self, torch):
+        n = self.n_own
+        self.h = [torch.empty(n * 16, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.sim.download_ptr(self.h[0].data_ptr(), n)
+
+    def e2e_step(self, i):
+        src, dst = self.h[i % 2], self.h[(i + 1) % 2]
+        self.sim.upload_ptr(src.data_ptr(), self.n_own)
+        self.sim.step(1)
+        self.sim.download_ptr(dst.data_ptr(), self.n_own)
+        return self.n_own * 64, self.n_own * 64, self.n_own
+
+    def last_host_state(self, i):
+        return self.h[i % 2].numpy().reshape(self.n_own, 16)
+
+
+class SlabRunner:
+    """N > 1: ONE global dam break (side*N x side x side particles) split into x slabs, one rank
+    per GPU, ghost halo exchange + migration over NCCL send/recv every step."""
+
+    def __init__(self, sph, O, args, rank, local, world, stream, torch, dist):
+        from nprsph_b200.dist import SlabGroup, unique_id
+        side = args.side
+        self.world = world
+        self.p = O.dam_break_params(side * world, side, side)
+        idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        self.grp = SlabGroup.nccl(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local,
+                                  stream=stream.cuda_stream, cell_subdiv=args.subdiv)
+        self.grp.apply_params(self.p)
+        self.grp.scene_block(side * world, side, side, 0.005, None, 1e-4 * 0.005, 1234)
+        self.grp.set_paused(False)
+        self.grp.step(1)                       # distributes the scene; part of the warm-up
+        info = self.grp.info()
+        self.n_own = int(info.num_own)
+        self.cap = int(info.cap_own)
+        st = self.grp.sims[0].stats()
+        self.grid_cells = (info.x_end - info.x_begin + 2 * st.cell_subdiv) * st.grid_dim[1] * st.grid_dim[2]
+        self.sort_passes = -(-max(1, int(self.grid_cells + 2).bit_length()) // 8)
+        # classify + hist + P onesweep + gather + 2 ghost keys + cells + fill + rho + force + integrate
+        self.launches_per_step = 10 + self.sort_passes
+        self.parallelism = (f"{world} slabs along x, 1 process/GPU, ghost halo (pos; v,rho) + migration "
+                            f"via ncclSend/ncclRecv each step")
+        self.api = "nprsph_dist_upload + nprsph_dist_step(1) + nprsph_dist_download, pinned host buffers"
+
+    def step(self, k):
+        self.grp.step(k)
+
+    def profile(self, k):
+        return self.grp.profile_step(k)
+
+    def alloc_host(self, torch):
+        self.h = [torch.empty(self.cap * 16, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.hid = [torch.empty(self.cap, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.n_host = self.grp.download_ptr(0, self.h[0].data_ptr(), self.hid[0].data_ptr(), self.cap)
+
+    def e2e_step(self, i):
+        a, b = i % 2, (i + 1) % 2
+        n_in = self.n_host
+        self.grp.upload_ptr(0, self.h[a].data_ptr(), self.hid[a].data_ptr(), n_in)
+        self.grp.step(1)
+        self.n_host = self.grp.download_ptr(0, self.h[b].data_ptr(), self.hid[b].data_ptr(), self.cap)
+        return n_in * 68, self.n_host * 68, n_in
+
+    def last_host_state(self, i):
+        return self.h[i % 2].numpy().reshape(self.cap, 16)[:self.n_host]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -135,111 +229,107 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libnprsph has no CPU path")
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    side = args.side
-    n_local = side ** 3
-    p = O.dam_break_params(side, side, side)
     stream = torch.cuda.Stream(device=local)
-    sim = sph.Simulation(device=local, stream=stream.cuda_stream, cell_subdiv=args.subdiv)
-    sim.apply_params(p)
-    sim.scene_block(side, side, side, 0.005, None, 1e-4 * 0.005, 1234)
-    sim.set_paused(False)
-    st = sim.stats()
-    launches_per_step = 6 + st.sort_passes    # hist + P onesweep + reorder + fill + rho + force + integrate
+    if world == 1:
+        run = SingleRunner(sph, O, args, local, stream)
+    else:
+        run = SlabRunner(sph, O, args, rank, local, world, stream, torch, dist)
+    n_total = args.side ** 3 * world
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     warm = max(args.warmup, 3)
-    with torch.cuda.stream(stream):
-        sim.step(warm)
-        barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        sim.step(args.steps)
-        e1.record(stream)
-        barrier()
-        clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run.step(warm)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0.record(stream)
+    run.step(args.steps)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms_total / args.steps
-    value = n_local * world * args.steps / (ms_total * 1e-3)
+    value = n_total * args.steps / (ms_total * 1e-3)
 
     # per-kernel device times (CUDA events between stages on the same stream), live
-    prof = sim.profile_step(max(3, min(args.steps, 10)))
+    prof = run.profile(max(3, min(args.steps, 10)))
+    n_k = run.n_own if world == 1 else int(run.grp.info().num_own)
     stage = max(ALGO_BYTES, key=lambda k: prof[k])
     peak, peak_src = peaks()
-    achieved = ALGO_BYTES[stage] * n_local / (prof[stage] * 1e-3) / 1e9
+    achieved = ALGO_BYTES[stage] * n_k / (prof[stage] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            tj = json.load(f)
-        key = f"{KERNEL_OF_STAGE[stage]}@{n_local}@subdiv{args.subdiv}"
-        traffic = tj.get(key)
+            traffic = json.load(f).get(f"{KERNEL_OF_STAGE[stage]}@{n_k}@subdiv{args.subdiv}")
     roofline = {"kernel": KERNEL_OF_STAGE[stage], "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": ALGO_BYTES[stage],
-                "kernel_ms": round(prof[stage], 4),
+                "particles_per_launch": n_k, "kernel_ms": round(prof[stage], 4),
                 "per_kernel_ms": {k: round(v, 4) for k, v in prof.items()},
-                "per_kernel_frac": {k: round(ALGO_BYTES[k] * n_local / (prof[k] * 1e-3) / 1e9 / peak, 4)
+                "per_kernel_frac": {k: round(ALGO_BYTES[k] * n_k / (prof[k] * 1e-3) / 1e9 / peak, 4)
                                     for k in ALGO_BYTES},
-                "step_frac": round(192 * n_local / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
+                "step_frac": round(192 * n_total / world / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                "note": "rho/force are instruction-issue bound (DESIGN.md 4); frac is algorithmic "
+                        "bytes / time / measured HBM peak, rank 0"}
 
     # end to end through the C ABI with HOST buffers: upload -> step -> download, every step
-    nbytes = n_local * 64
-    h_a = torch.empty(n_local * 16, dtype=torch.float32).pin_memory()
-    h_b = torch.empty(n_local * 16, dtype=torch.float32).pin_memory()
-    sim.download_ptr(h_a.data_ptr(), n_local)
-    with torch.cuda.stream(stream):
-        sim.upload_ptr(h_a.data_ptr(), n_local); sim.step(1); sim.download_ptr(h_b.data_ptr(), n_local)
-        barrier()
-        e0.record(stream)
-        src, dst = h_b, h_a
-        for _ in range(args.e2e_steps):
-            sim.upload_ptr(src.data_ptr(), n_local)
-            sim.step(1)
-            sim.download_ptr(dst.data_ptr(), n_local)
-            src, dst = dst, src
-        e1.record(stream)
-        barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n_local * world * args.e2e_steps / (float(t.item()) * 1e-3)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
-           "d2h_bytes_per_step": nbytes * world, "steps": args.e2e_steps,
-           "api": "nprsph_upload_particles + nprsph_step(1) + nprsph_download_particles, pinned host buffers"}
+    run.alloc_host(torch)
+    run.e2e_step(0)
+    barrier()
+    e0.record(stream)
+    h2d = d2h = 0
+    for i in range(1, args.e2e_steps + 1):
+        a, b, _ = run.e2e_step(i)
+        h2d, d2h = h2d + a, d2h + b
+    e1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"value": n_total * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int(sum_over_ranks(h2d) / args.e2e_steps),
+           "d2h_bytes_per_step": int(sum_over_ranks(d2h) / args.e2e_steps),
+           "steps": args.e2e_steps, "api": run.api}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import numpy as np
-        host = src.numpy().reshape(n_local, 16)      # last downloaded state (carries rho/p)
-        cpu_baseline = cpu_sample(O, np.ascontiguousarray(host), p, budget_s=12.0)
+        host = np.ascontiguousarray(run.last_host_state(args.e2e_steps + 1))   # carries rho/p
+        cpu_baseline = cpu_sample(O, host, run.p, budget_s=12.0)
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": f"dam_break_{n_local}_per_gpu_fp32 (side {side}, h=2s, "
-                                      f"stable recipe SURVEY 8(d), jitter seed 1234)",
-                          "particles_total": n_local * world, "cell_subdiv": args.subdiv,
-                          "grid_cells": st.num_cells, "sort_passes": st.sort_passes,
-                          "parallelism": "1 process/GPU" if world == 1 else
-                                         f"{world} independent replicas, one per GPU (no data-path collective)",
-                          "l2": "working set per step (>2 GB) exceeds the 126 MB L2; no flush needed"},
-               "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+               "config": {"workload": f"dam_break_{args.side ** 3}_per_gpu_fp32 (block {args.side * world}x"
+                                      f"{args.side}x{args.side}, h=2s, stable recipe SURVEY 8(d), jitter seed 1234)",
+                          "particles_total": n_total, "cell_subdiv": args.subdiv,
+                          "grid_cells_per_rank": int(run.grid_cells), "sort_passes": int(run.sort_passes),
+                          "parallelism": run.parallelism,
+                          "l2": "working set per step (>2 GB per GPU) exceeds the 126 MB L2; no flush needed"},
+               "roofline": roofline, "e2e": e2e, "gpu_launches": run.launches_per_step * args.steps,
                "clocks": clocks}
         if cpu_baseline:
             out["cpu_baseline"] = cpu_baseline

@@ -226,6 +226,11 @@ int nprsph_dist_step(nprsph_ctx** ranks, int n_local, int steps);
 /* collective; copies the own particles of ranks[which] (records + their global indices) */
 int nprsph_dist_download(nprsph_ctx** ranks, int n_local, int which, nprsph_particle* records,
                          uint32_t* ids, uint64_t capacity, uint64_t* n_out);
+/* replaces the own particles of this rank by host records + global indices (restart / e2e);
+ * records whose position lies outside the rank's slab are dropped */
+int nprsph_dist_upload(nprsph_ctx* ctx, const nprsph_particle* records, const uint32_t* ids, uint64_t n);
+/* collective nprsph_profile_step(): SORT = whole prepare phase, REORDER = (v, rho) halo exchange */
+int nprsph_dist_profile_step(nprsph_ctx** ranks, int n_local, int steps, float* stage_ms);
 int nprsph_dist_get_info(nprsph_ctx* ctx, nprsph_dist_info* out);
 
 #ifdef __cplusplus

@@ -48,7 +48,7 @@ float r2_threshold(float h) {
 
 // Uniform-grid definition (DESIGN.md "Grid"): cell = h*(1+2^-10)/subdiv, widened when an axis
 // would exceed 2048 cells or the table would exceed max_cells.
-int setup_grid(const nprsph_ctx* c, float h, GridDev* g, float* cell_size) {
+int setup_grid(const nprsph_ctx* c, float h, int slab_ranks, GridDev* g, float* cell_size) {
     int k = c->cfg.cell_subdiv;
     if (!(h > 0.0f) || isinf(h) || k < 1 || k > 4) return -1;
     double ext[3];
@@ -57,24 +57,29 @@ int setup_grid(const nprsph_ctx* c, float h, GridDev* g, float* cell_size) {
         if (!(e == e) || isinf(e)) return -2;
         ext[a] = e > 0.0 ? e : 0.0;
     }
-    uint32_t max_cells = c->cfg.max_cells ? c->cfg.max_cells : (1u << 28);
-    double cell = (double)h * (1.0 + 1.0 / 1024.0) / (double)k;
+    // slab mode: the cap applies to a rank's share of the table, not to the global grid
+    double max_cells = (double)(c->cfg.max_cells ? c->cfg.max_cells : (1u << 28)) * (double)slab_ranks;
+    // cell = base * (1 + widen).  `widen` keeps `reach` cells sufficient under the fp32 rounding of
+    // the cell coordinate (error <= dim * 2^-23 cells): widen >= dim_max * 2^-21, at least 2^-10.
+    double base = (double)h / (double)k, widen = 1.0 / 1024.0, cell = 0.0;
     double dims[3] = {1, 1, 1};
     for (int iter = 0; iter < 64; iter++) {
-        bool again = false;
+        cell = base * (1.0 + widen);
+        double dmax = 1.0;
         for (int a = 0; a < 3; a++) {
             dims[a] = floor(ext[a] / cell) + 1.0;
-            if (dims[a] > 2048.0) { cell = ext[a] / 2047.0; again = true; break; }
+            if (dims[a] > dmax) dmax = dims[a];
         }
-        if (again) continue;
-        double total = dims[0] * dims[1] * dims[2];
-        if (total > (double)max_cells) { cell *= cbrt(total / (double)max_cells) * 1.0001; continue; }
+        if (dmax > 16384.0) { base *= dmax / 16383.0 * 1.0001; continue; }
+        if (dmax / 2097152.0 > widen) { widen *= 2.0; continue; }
+        const double total = dims[0] * dims[1] * dims[2];
+        if (total > max_cells) { base *= cbrt(total / max_cells) * 1.0001; continue; }
         break;
     }
     for (int a = 0; a < 3; a++) { g->lo[a] = c->bounds.lower[a]; g->dim[a] = (int)dims[a]; }
     g->inv_cell = (float)(1.0 / cell);
     g->reach = k;
-    g->num_cells = (uint32_t)((int64_t)g->dim[0] * g->dim[1] * g->dim[2]);
+    g->num_cells = (uint32_t)((int64_t)g->dim[0] * g->dim[1] * g->dim[2]);   // (wraps in slab mode: unused there)
     g->x_off = 0;
     g->dimx_global = g->dim[0];
     *cell_size = (float)cell;
@@ -106,23 +111,26 @@ int nprsph::refresh_params(nprsph_ctx* c) {
 
     GridDev g;
     float cell_size;
-    if (setup_grid(c, s.h, &g, &cell_size))
+    if (setup_grid(c, s.h, slab_world(c), &g, &cell_size))
         return fail(c, NPRSPH_ERR_INVALID, "cannot build a grid: smoothing length or bounds invalid%s");
-    {   // column cull threshold: h in cell units plus a margin far above the fp32 error of the
-        // cell coordinates (<= 2^-12 cells for <= 2048 cells per axis)
-        const float hc = s.h * g.inv_cell + 1.0f / 256.0f;
+    {   // column cull threshold: h in cell units plus a margin above twice the fp32 error of the
+        // cell coordinates (<= dim * 2^-23 cells each)
+        int dmax = g.dim[0] > g.dim[1] ? g.dim[0] : g.dim[1];
+        if (g.dim[2] > dmax) dmax = g.dim[2];
+        const float margin = fmaxf(1.0f / 256.0f, (float)dmax / 1048576.0f);
+        const float hc = s.h * g.inv_cell + margin;
         s.cull2 = hc * hc;
     }
     c->mask_valid = false;
     if (memcmp(&g, &c->grid, sizeof g) != 0) { c->keys_valid = false; c->grid_valid = false; }
-    const size_t need = (size_t)g.num_cells + 2;
+    const size_t need = c->dist ? 0 : (size_t)g.num_cells + 2;   // slab mode sizes its own local table
     if (need > c->cell_cap) {
         if (c->cell_start) CK(c, cudaFree(c->cell_start));
         c->cell_start = nullptr; c->cell_cap = 0;
         CK(c, cudaMalloc(&c->cell_start, need * sizeof(uint32_t)));
         c->cell_cap = need;
     }
-    const size_t gaps = gap_list_capacity(g.num_cells, c->cap ? c->cap : 1);
+    const size_t gaps = c->dist ? 0 : gap_list_capacity(g.num_cells, c->cap ? c->cap : 1);
     if (gaps > c->gap_cap) {
         if (c->gap_list) CK(c, cudaFree(c->gap_list));
         c->gap_list = nullptr; c->gap_cap = 0;

@@ -93,5 +93,6 @@ cudaError_t realloc_dev(T*& p, size_t count) {
 
 // dist.cu
 void dist_destroy(nprsph_ctx* c);
+int slab_world(const nprsph_ctx* c);      // number of slab ranks (1 without nprsph_dist_init)
 
 }  // namespace nprsph

@@ -266,6 +266,21 @@ k_pack_records(const float4* __restrict__ posid, const float4* __restrict__ velr
     ids[s] = __float_as_uint(p.w);
 }
 
+// host records + ids (nprsph_dist_upload) -> own slots and slab keys
+__global__ void __launch_bounds__(TPB)
+k_unpack_records(const float4* __restrict__ rec, const uint32_t* __restrict__ ids, uint32_t n,
+                 float4* __restrict__ posid, float4* __restrict__ velrho, float4* __restrict__ forcep,
+                 uint32_t* __restrict__ keys, GridDev g, int W, int R) {
+    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    if (s >= n) return;
+    const float4 p = rec[4 * (size_t)s], v = rec[4 * (size_t)s + 1], f = rec[4 * (size_t)s + 2];
+    const float4 e = rec[4 * (size_t)s + 3];
+    posid[s] = make_float4(p.x, p.y, p.z, __uint_as_float(ids[s]));
+    velrho[s] = make_float4(v.x, v.y, v.z, e.x);
+    forcep[s] = make_float4(f.x, f.y, f.z, e.y);
+    keys[s] = cell_key_slab(p.x, p.y, p.z, g, W, R);
+}
+
 // ---- neighbour exchange --------------------------------------------------------------------------
 // Sends sendL/sendR to the left/right rank and receives recvL/recvR from them (byte counts; a
 // rank at the end of the chain has no neighbour on that side).  LOCAL transport: the "ranks" are
@@ -505,10 +520,14 @@ int ensure_prepared(nprsph_ctx** cs, int n) {
     return NPRSPH_OK;
 }
 
-int step_group(nprsph_ctx** cs, int n) {
+// ev (nullable): 5 events recorded on rank 0's stream at the stage boundaries
+// [prepare | rho | halo(v,rho) | force | integrate]
+int step_group(nprsph_ctx** cs, int n, cudaEvent_t* ev = nullptr) {
     Xfer x[64];
+    if (ev) CK(cs[0], cudaEventRecord(ev[0], cs[0]->stream));
     int rc = ensure_prepared(cs, n);
     if (rc) return rc;
+    if (ev) CK(cs[0], cudaEventRecord(ev[1], cs[0]->stream));
     for (int r = 0; r < n; r++) {
         nprsph_ctx* c = cs[r]; DistState* d = c->dist;
         CK(c, cudaSetDevice(c->cfg.device));
@@ -521,13 +540,16 @@ int step_group(nprsph_ctx** cs, int n) {
                 v + d->own_off - d->gL, d->gL * sizeof(float4),
                 v + d->own_off + d->n_own, d->gR * sizeof(float4)};
     }
+    if (ev) CK(cs[0], cudaEventRecord(ev[2], cs[0]->stream));
     rc = exchange_group(cs, n, x);                 // (velocity, rho) of the boundary layers
     if (rc) return rc;
+    if (ev) CK(cs[0], cudaEventRecord(ev[3], cs[0]->stream));
     for (int r = 0; r < n; r++) {
         nprsph_ctx* c = cs[r]; DistState* d = c->dist;
         CK(c, cudaSetDevice(c->cfg.device));
         launch_force(c->pos[c->cur], c->vel[c->cur], c->frc[0], c->cell_start, d->own_off, d->n_own,
                      d->lg, c->sph, nullptr, c->hitmask, d->cap_total, c->stream);
+        if (ev && r == 0) CK(c, cudaEventRecord(ev[4], c->stream));
         if (d->n_own)
             k_integrate_slab<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
                 c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off,
@@ -555,6 +577,8 @@ int check_group(nprsph_ctx** cs, int n) {
 }
 
 }  // namespace
+
+int nprsph::slab_world(const nprsph_ctx* c) { return c->dist ? c->dist->world : 1; }
 
 void nprsph::dist_destroy(nprsph_ctx* c) {
     DistState* d = c->dist;
@@ -758,6 +782,54 @@ int nprsph_dist_download(nprsph_ctx** ranks, int n_local, int which, nprsph_part
     }
     CK(c, cudaStreamSynchronize(c->stream));
     return NPRSPH_OK;
+}
+
+int nprsph_dist_upload(nprsph_ctx* c, const nprsph_particle* records, const uint32_t* ids, uint64_t n) {
+    GUARD(c);
+    DistState* d = c->dist;
+    if (!d || !d->ready) return fail(c, NPRSPH_ERR_STATE, "distribute a scene first (slab geometry and capacities)%s");
+    if (n > d->cap_own || (n && (!records || !ids))) return fail(c, NPRSPH_ERR_INVALID, "bad upload%s");
+    if (n) {
+        uint32_t* d_ids = c->vals[1];
+        CK(c, cudaMemcpyAsync(c->aos, records, n * 64, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(d_ids, ids, n * 4, cudaMemcpyHostToDevice, c->stream));
+        k_unpack_records<<<blocks_for(n), TPB, 0, c->stream>>>(
+            (const float4*)c->aos, d_ids, (uint32_t)n, c->pos[c->cur] + d->own_off,
+            c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off, c->keys[0], d->lg, d->W, d->R);
+        CK(c, cudaGetLastError());
+    }
+    d->n_own = (uint32_t)n;
+    d->first_prepare = true;         // records that belong to another slab are dropped, not sent
+    d->prepared = false;
+    return NPRSPH_OK;
+}
+
+int nprsph_dist_profile_step(nprsph_ctx** ranks, int n_local, int steps, float* stage_ms) {
+    int rc = check_group(ranks, n_local);
+    if (rc) return rc;
+    if (steps < 1 || !stage_ms) return NPRSPH_ERR_INVALID;
+    nprsph_ctx* c0 = ranks[0];
+    CK(c0, cudaSetDevice(c0->cfg.device));
+    cudaEvent_t ev[6];
+    for (int i = 0; i < 6; i++) CK(c0, cudaEventCreate(&ev[i]));
+    double acc[NPRSPH_NUM_STAGES] = {0};
+    for (int s = 0; s < steps && rc == NPRSPH_OK; s++) {
+        rc = step_group(ranks, n_local, ev);
+        if (rc) break;
+        CK(c0, cudaEventRecord(ev[5], c0->stream));
+        for (int r = 0; r < n_local; r++) CK(ranks[r], cudaStreamSynchronize(ranks[r]->stream));
+        // prepare (classify..sort..halo..table) is reported as SORT, the (v, rho) halo as REORDER
+        const int stage_of[5] = {NPRSPH_STAGE_SORT, NPRSPH_STAGE_RHO, NPRSPH_STAGE_REORDER,
+                                 NPRSPH_STAGE_FORCE, NPRSPH_STAGE_INTEGRATE};
+        for (int i = 0; i < 5; i++) {
+            float ms = 0.f;
+            CK(c0, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            acc[stage_of[i]] += ms;
+        }
+    }
+    for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
+    for (int i = 0; i < NPRSPH_NUM_STAGES; i++) stage_ms[i] = (float)(acc[i] / steps);
+    return rc;
 }
 
 int nprsph_dist_get_info(nprsph_ctx* c, nprsph_dist_info* out) {

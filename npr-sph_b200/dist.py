@@ -129,6 +129,21 @@ class SlabGroup:
                                                ids.ctypes.data, n.value, C.byref(n)))
         return rec, ids
 
+    def download_ptr(self, which, rec_ptr: int, ids_ptr: int, capacity: int) -> int:
+        n = C.c_uint64()
+        self._ck(self.lib.nprsph_dist_download(self._arr, len(self.sims), which, rec_ptr, ids_ptr,
+                                               capacity, C.byref(n)))
+        return n.value
+
+    def upload_ptr(self, which, rec_ptr: int, ids_ptr: int, n: int):
+        s = self.sims[which]
+        s._ck(s.lib.nprsph_dist_upload(s._h, rec_ptr, ids_ptr, n))
+
+    def profile_step(self, n_steps=1) -> dict:
+        ms = (C.c_float * len(B.STAGES))()
+        self._ck(self.lib.nprsph_dist_profile_step(self._arr, len(self.sims), n_steps, ms))
+        return {k: float(ms[i]) for i, k in enumerate(B.STAGES)}
+
     def gather(self, n_global: int) -> np.ndarray:
         """All local ranks' particles placed by global index (LOCAL transport: the whole scene)."""
         out = np.full((n_global, 16), np.nan, np.float32)

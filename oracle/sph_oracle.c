@@ -298,17 +298,21 @@ int oracle_grid_setup(const oracle_params* p, int k, uint32_t max_cells, oracle_
         ext[a] = e > 0.0 ? e : 0.0;
     }
     if (max_cells == 0) max_cells = 1u << 28;
-    double cell = (double)h * (1.0 + 1.0 / 1024.0) / (double)k;
-    double dims[3];
+    /* cell = base * (1 + widen); widen >= dim_max * 2^-21 (at least 2^-10) keeps `reach` cells
+     * sufficient under the fp32 rounding of the cell coordinate (DESIGN.md "Grid") */
+    double base = (double)h / (double)k, widen = 1.0 / 1024.0, cell = 0.0;
+    double dims[3] = {1, 1, 1};
     for (int iter = 0; iter < 64; iter++) {
-        int again = 0;
+        cell = base * (1.0 + widen);
+        double dmax = 1.0;
         for (int a = 0; a < 3; a++) {
             dims[a] = floor(ext[a] / cell) + 1.0;
-            if (dims[a] > 2048.0) { cell = ext[a] / 2047.0; again = 1; break; }
+            if (dims[a] > dmax) dmax = dims[a];
         }
-        if (again) continue;
+        if (dmax > 16384.0) { base *= dmax / 16383.0 * 1.0001; continue; }
+        if (dmax / 2097152.0 > widen) { widen *= 2.0; continue; }
         double total = dims[0] * dims[1] * dims[2];
-        if (total > (double)max_cells) { cell *= cbrt(total / (double)max_cells) * 1.0001; continue; }
+        if (total > (double)max_cells) { base *= cbrt(total / (double)max_cells) * 1.0001; continue; }
         break;
     }
     for (int a = 0; a < 3; a++) { g->lo[a] = p->lower[a]; g->dim[a] = (int32_t)dims[a]; }
