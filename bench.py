@@ -37,8 +37,8 @@ KERNEL_OF_STAGE = {"rho": "k_rho", "force": "k_force", "integrate": "k_integrate
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=256, help="lattice block is side^3 particles per GPU")
     ap.add_argument("--subdiv", type=int, default=2, help="grid cells per smoothing length")
@@ -77,7 +77,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Wall-clock marker: call at the start and at the end of the timed region."""
+        self.marks = getattr(self, "marks", []) + [time.time()]
 
     def stop(self) -> dict:
         if not self.proc:
@@ -89,7 +93,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        marks = getattr(self, "marks", [])
+        lines, window = self.lines, "sampler lifetime (warm-up + timed region, same workload)"
+        if len(marks) == 2:
+            inside = [x for x in self.lines if marks[0] <= x[0] <= marks[1] + 0.15]
+            if len(inside) >= 2:
+                lines, window = inside, "timed region"
+        for _, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -101,7 +111,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "window": window,
                 "reasons": sorted(reasons)}
 
 
@@ -260,14 +270,16 @@ def run_ours(args):
 
     warm = max(args.warmup, 3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()                    # nvidia-smi needs ~0.1 s to deliver its first sample
     run.step(warm)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     e0.record(stream)
     run.step(args.steps)
     e1.record(stream)
     barrier()
+    sampler.mark()
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms_total / args.steps
