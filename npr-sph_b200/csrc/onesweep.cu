@@ -147,10 +147,24 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     uint32_t rank[SORT_ITEMS];
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* my_hist = s_warp_hist[warp];
+    // Cell-ordered keys share their upper digits over long runs: when a whole row of 32 keys has
+    // one digit (two REDUX votes), the match-any vote -- the slowest instruction of the kernel --
+    // is skipped.
     uint32_t peers[SORT_ITEMS];
 #pragma unroll
-    for (int k = 0; k < SORT_ITEMS; k++)
-        peers[k] = __match_any_sync(0xffffffffu, (key[k] >> shift) & mask);
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        // MATCH.ANY costs one round per distinct value in the warp.  Cell-ordered keys give rows
+        // whose digits are either all equal or count upwards (consecutive cells; after the first
+        // pass, keys 256 apart), i.e. all distinct: both cases are recognised with two shuffles
+        // and a vote, and only irregular rows pay for the match.
+        const uint32_t d = (key[k] >> shift) & mask;
+        const uint32_t e = (d - __shfl_sync(0xffffffffu, d, 0)) & mask;     // offset from lane 0, cyclic
+        const uint32_t below_e = __shfl_up_sync(0xffffffffu, e, 1);
+        const bool rising = lane == 0 || e > below_e;
+        if (!__any_sync(0xffffffffu, e != 0u))      peers[k] = 0xffffffffu;           // one digit
+        else if (__all_sync(0xffffffffu, rising))   peers[k] = 1u << lane;            // all distinct
+        else                                        peers[k] = __match_any_sync(0xffffffffu, d);
+    }
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; k++) {
         const uint32_t d = (key[k] >> shift) & mask;

@@ -23,7 +23,11 @@ def run(n1, subdiv, steps=10, coeff=2.0, flags=0):
                       "dim": list(st.grid_dim), "key_bits": st.key_bits, "nan": st.nan_particles}))
 
 if __name__ == "__main__":
+    import os
+    only = os.environ.get("QP_ONLY")            # "subdiv,flags" to run a single configuration
     for n1 in [int(a) for a in sys.argv[1:]] or [100, 256]:
         for subdiv in (1, 2):
             for flags in (0, 2):
+                if only and only != f"{subdiv},{flags}":
+                    continue
                 run(n1, subdiv, flags=flags)
