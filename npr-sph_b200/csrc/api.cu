@@ -122,7 +122,10 @@ int nprsph::refresh_params(nprsph_ctx* c) {
         s.cull2 = hc * hc;
     }
     c->mask_valid = false;
-    if (memcmp(&g, &c->grid, sizeof g) != 0) { c->keys_valid = false; c->grid_valid = false; }
+    if (memcmp(&g, &c->grid, sizeof g) != 0) {
+        c->keys_valid = false; c->grid_valid = false;
+        CK(c, cudaMemsetAsync(c->gap_count + 4, 0xFF, 8, c->stream));   // cell table contents are void
+    }
     const size_t need = c->dist ? 0 : (size_t)g.num_cells + 2;   // slab mode sizes its own local table
     if (need > c->cell_cap) {
         if (c->cell_start) CK(c, cudaFree(c->cell_start));
@@ -371,7 +374,8 @@ int nprsph_create(const nprsph_config* cfg, nprsph_ctx** out) {
         if (e != cudaSuccess) { delete c; return fail(nullptr, NPRSPH_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         c->own_stream = true;
     }
-    e = cudaMalloc(&c->gap_count, 16);
+    e = cudaMalloc(&c->gap_count, 32);    // [0] gap count, [2..3] NaN counter, [4..5] tail state of the cell table
+    if (e == cudaSuccess) e = cudaMemset(c->gap_count, 0xFF, 32);
     if (e != cudaSuccess) { nprsph_destroy(c); return fail(nullptr, NPRSPH_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
     int rc = build_scene(c);      // initOpenGL() -> init_particles(), Main.cpp:567
     if (rc) { g_create_error = c->err; nprsph_destroy(c); return rc; }

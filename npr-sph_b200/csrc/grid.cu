@@ -68,7 +68,8 @@ k_reorder_cells(const uint32_t* __restrict__ sorted_keys, const uint32_t* __rest
                 const float4* __restrict__ force_in, float4* __restrict__ pos_out,
                 float4* __restrict__ vel_out, float4* __restrict__ force_out,
                 uint32_t* __restrict__ cell_start, uint32_t num_cells, uint32_t n,
-                uint4* __restrict__ gap_list, uint32_t* __restrict__ gap_count) {
+                uint4* __restrict__ gap_list, uint32_t* __restrict__ gap_count,
+                uint32_t* __restrict__ tail_state) {
     const uint32_t s = blockIdx.x * TPB + threadIdx.x;
     if (s > n) return;
     uint32_t key_here;
@@ -83,6 +84,17 @@ k_reorder_cells(const uint32_t* __restrict__ sorted_keys, const uint32_t* __rest
     }
     const uint32_t lo = (s == 0) ? 0u : sorted_keys[s - 1] + 1u;
     if (key_here < lo) return;                    // same cell as the previous slot
+    if (s == n) {
+        // Tail (every cell above the last key holds n).  In a dam break that is most of the table;
+        // tail_state = {F, V} records that cells >= F already hold V from an earlier step, so only
+        // the cells the fluid vacated since then are rewritten.
+        const uint32_t F = tail_state[0], V = tail_state[1];
+        tail_state[0] = lo; tail_state[1] = n;
+        if (V == n) {
+            if (F <= lo) return;
+            if (F <= key_here) key_here = F - 1u;
+        }
+    }
     const uint32_t len = key_here - lo + 1u;
     if (len <= GAP_INLINE) {
         for (uint32_t c = lo; c <= key_here; c++) cell_start[c] = s;
@@ -149,10 +161,10 @@ void launch_reorder_cells(const uint32_t* sorted_keys, const uint32_t* perm, con
     const unsigned blocks = blocks_for((uint64_t)n + 1, TPB);
     if (with_force)
         k_reorder_cells<true><<<blocks, TPB, 0, st>>>(sorted_keys, perm, pos_in, vel_in, force_in,
-            pos_out, vel_out, force_out, cell_start, num_cells, n, gap_list, gap_count);
+            pos_out, vel_out, force_out, cell_start, num_cells, n, gap_list, gap_count, gap_count + 4);
     else
         k_reorder_cells<false><<<blocks, TPB, 0, st>>>(sorted_keys, perm, pos_in, vel_in, force_in,
-            pos_out, vel_out, force_out, cell_start, num_cells, n, gap_list, gap_count);
+            pos_out, vel_out, force_out, cell_start, num_cells, n, gap_list, gap_count, gap_count + 4);
     k_fill_gaps<<<num_sms * 4, TPB, 0, st>>>(gap_list, gap_count, cell_start);
 }
 
