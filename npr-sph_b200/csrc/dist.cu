@@ -288,19 +288,19 @@ k_unpack_records(const float4* __restrict__ rec, const uint32_t* __restrict__ id
 // neighbour's send pointer; the group driver posts all sends before any receive runs.
 struct Posted { const void* toL = nullptr; const void* toR = nullptr; };
 
-int exchange_nccl(nprsph_ctx* c, const void* sendL, size_t nL, const void* sendR, size_t nR,
-                  void* recvL, size_t rL, void* recvR, size_t rR) {
+int exchange_nccl(nprsph_ctx* c, cudaStream_t st, const void* sendL, size_t nL, const void* sendR,
+                  size_t nR, void* recvL, size_t rL, void* recvR, size_t rR) {
     DistState* d = c->dist;
     NcclApi* api = nccl();
     ncclComm_t comm = (ncclComm_t)d->nccl_comm;
     NCK(c, api->GroupStart());
     if (d->rank > 0) {
-        if (nL) NCK(c, api->Send(sendL, nL, ncclChar, d->rank - 1, comm, c->stream));
-        if (rL) NCK(c, api->Recv(recvL, rL, ncclChar, d->rank - 1, comm, c->stream));
+        if (nL) NCK(c, api->Send(sendL, nL, ncclChar, d->rank - 1, comm, st));
+        if (rL) NCK(c, api->Recv(recvL, rL, ncclChar, d->rank - 1, comm, st));
     }
     if (d->rank + 1 < d->world) {
-        if (nR) NCK(c, api->Send(sendR, nR, ncclChar, d->rank + 1, comm, c->stream));
-        if (rR) NCK(c, api->Recv(recvR, rR, ncclChar, d->rank + 1, comm, c->stream));
+        if (nR) NCK(c, api->Send(sendR, nR, ncclChar, d->rank + 1, comm, st));
+        if (rR) NCK(c, api->Recv(recvR, rR, ncclChar, d->rank + 1, comm, st));
     }
     NCK(c, api->GroupEnd());
     return NPRSPH_OK;
@@ -308,18 +308,22 @@ int exchange_nccl(nprsph_ctx* c, const void* sendL, size_t nL, const void* sendR
 
 struct Xfer { const void* sendL; size_t nL; const void* sendR; size_t nR; void* recvL; size_t rL; void* recvR; size_t rR; };
 
-int exchange_group(nprsph_ctx** cs, int n, const Xfer* x) {
+// on_comm: run the transfers on each rank's communication stream (the caller orders it against
+// the compute stream with events) instead of the compute stream
+int exchange_group(nprsph_ctx** cs, int n, const Xfer* x, bool on_comm = false) {
+    auto stream_of = [&](nprsph_ctx* c) { return on_comm ? c->dist->comm_stream : c->stream; };
     if (n == 1 && cs[0]->dist->transport == NPRSPH_TRANSPORT_NCCL)
-        return exchange_nccl(cs[0], x[0].sendL, x[0].nL, x[0].sendR, x[0].nR, x[0].recvL, x[0].rL, x[0].recvR, x[0].rR);
+        return exchange_nccl(cs[0], stream_of(cs[0]), x[0].sendL, x[0].nL, x[0].sendR, x[0].nR, x[0].recvL,
+                             x[0].rL, x[0].recvR, x[0].rR);
     for (int r = 0; r < n; r++) {          // LOCAL: rank r receives from r-1 (its sendR) and r+1 (its sendL)
         nprsph_ctx* c = cs[r];
         if (r > 0 && x[r].rL) {
             if (x[r].rL != x[r - 1].nR) return fail(c, NPRSPH_ERR_COMM, "local exchange size mismatch%s");
-            CK(c, cudaMemcpyAsync(x[r].recvL, x[r - 1].sendR, x[r].rL, cudaMemcpyDeviceToDevice, c->stream));
+            CK(c, cudaMemcpyAsync(x[r].recvL, x[r - 1].sendR, x[r].rL, cudaMemcpyDeviceToDevice, stream_of(c)));
         }
         if (r + 1 < n && x[r].rR) {
             if (x[r].rR != x[r + 1].nL) return fail(c, NPRSPH_ERR_COMM, "local exchange size mismatch%s");
-            CK(c, cudaMemcpyAsync(x[r].recvR, x[r + 1].sendL, x[r].rR, cudaMemcpyDeviceToDevice, c->stream));
+            CK(c, cudaMemcpyAsync(x[r].recvR, x[r + 1].sendL, x[r].rR, cudaMemcpyDeviceToDevice, stream_of(c)));
         }
     }
     return NPRSPH_OK;
@@ -356,6 +360,7 @@ int setup_local_grid(nprsph_ctx* c) {
 
 int alloc_slab(nprsph_ctx* c, uint64_t cap_own, uint64_t cap_ghost, uint64_t cap_mig) {
     DistState* d = c->dist;
+    cap_ghost = (cap_ghost + 1) & ~(uint64_t)1;      // own_off even: slot pairs are (even, odd)
     const uint64_t total = cap_own + 2 * cap_ghost;
     if (total >= (1ull << 30)) return fail(c, NPRSPH_ERR_INVALID, "slab capacity too large%s");
     CK(c, cudaStreamSynchronize(c->stream));
@@ -541,14 +546,34 @@ int step_group(nprsph_ctx** cs, int n, cudaEvent_t* ev = nullptr) {
                 v + d->own_off + d->n_own, d->gR * sizeof(float4)};
     }
     if (ev) CK(cs[0], cudaEventRecord(ev[2], cs[0]->stream));
-    rc = exchange_group(cs, n, x);                 // (velocity, rho) of the boundary layers
+    // (velocity, rho) of the boundary layers travels on the communication streams while the
+    // compute stream runs the force pass for the interior slots, whose walks touch no ghost cell;
+    // the two boundary layers (and the NaN block) follow once the ghosts' (v, rho) have landed.
+    // Range edges are even slots so that the slot pairs of k_rho / k_force_mask stay aligned.
+    for (int r = 0; r < n; r++) CK(cs[r], cudaEventRecord(cs[r]->dist->ev_rho, cs[r]->stream));
+    for (int r = 0; r < n; r++)                    // LOCAL: ranks share one compute stream, so the
+        CK(cs[r], cudaStreamWaitEvent(cs[r]->dist->comm_stream, cs[n - 1]->dist->ev_rho, 0));   // last event covers all
+    rc = exchange_group(cs, n, x, true);
     if (rc) return rc;
+    for (int r = 0; r < n; r++) CK(cs[r], cudaEventRecord(cs[r]->dist->ev_halo, cs[r]->dist->comm_stream));
     if (ev) CK(cs[0], cudaEventRecord(ev[3], cs[0]->stream));
     for (int r = 0; r < n; r++) {
         nprsph_ctx* c = cs[r]; DistState* d = c->dist;
         CK(c, cudaSetDevice(c->cfg.device));
-        launch_force(c->pos[c->cur], c->vel[c->cur], c->frc[0], c->cell_start, d->own_off, d->n_own,
-                     d->lg, c->sph, nullptr, c->hitmask, d->cap_total, c->stream);
+        const uint32_t own_end = d->own_off + d->n_own;
+        const uint32_t right0 = own_end - d->n_nan - d->hR;
+        uint32_t in0 = (d->rank > 0) ? ((d->own_off + d->hL + 1u) & ~1u) : d->own_off;
+        uint32_t in1 = (d->rank + 1 < d->world) ? (right0 & ~1u) : own_end;
+        if (in0 > own_end) in0 = own_end;
+        if (in1 < in0) in1 = in0;
+        const float4* P = c->pos[c->cur]; const float4* V = c->vel[c->cur];
+        launch_force(P, V, c->frc[0], c->cell_start, in0, in1 - in0, d->lg, c->sph, nullptr, c->hitmask,
+                     d->cap_total, c->stream);
+        for (int q = 0; q < n; q++) CK(c, cudaStreamWaitEvent(c->stream, cs[q]->dist->ev_halo, 0));
+        launch_force(P, V, c->frc[0], c->cell_start, d->own_off, in0 - d->own_off, d->lg, c->sph, nullptr,
+                     c->hitmask, d->cap_total, c->stream);
+        launch_force(P, V, c->frc[0], c->cell_start, in1, own_end - in1, d->lg, c->sph, nullptr,
+                     c->hitmask, d->cap_total, c->stream);
         if (ev && r == 0) CK(c, cudaEventRecord(ev[4], c->stream));
         if (d->n_own)
             k_integrate_slab<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
@@ -587,6 +612,9 @@ void nprsph::dist_destroy(nprsph_ctx* c) {
     cudaFree(d->sendL); cudaFree(d->sendR); cudaFree(d->recv); cudaFree(d->skeys);
     cudaFree(d->d_counts); cudaFree(d->mig_ids); cudaFree(d->mig_sort_ws);
     if (d->h_counts) cudaFreeHost(d->h_counts);
+    if (d->comm_stream) { cudaStreamSynchronize(d->comm_stream); cudaStreamDestroy(d->comm_stream); }
+    if (d->ev_rho) cudaEventDestroy(d->ev_rho);
+    if (d->ev_halo) cudaEventDestroy(d->ev_halo);
     delete d;
     c->dist = nullptr;
 }
@@ -638,6 +666,9 @@ int nprsph_dist_init(nprsph_ctx* c, const nprsph_dist_config* cfg) {
     c->dist = d;
     CK(c, cudaMalloc(&d->d_counts, 3 * CNT_WORDS * sizeof(uint32_t)));
     CK(c, cudaMallocHost(&d->h_counts, 3 * CNT_WORDS * sizeof(uint32_t)));
+    CK(c, cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
+    CK(c, cudaEventCreateWithFlags(&d->ev_rho, cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming));
     if (cfg->transport == NPRSPH_TRANSPORT_NCCL && cfg->world > 1) {
         NcclApi* api = nccl();
         if (!api) return fail(c, NPRSPH_ERR_UNSUPPORTED, "libnccl.so.2 not found%s");

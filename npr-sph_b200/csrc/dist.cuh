@@ -14,6 +14,8 @@ struct DistState {
     int rank = 0, world = 1;
     int transport = 0;                 // NPRSPH_TRANSPORT_*
     void* nccl_comm = nullptr;
+    cudaStream_t comm_stream = nullptr;   // halo traffic that overlaps the interior force pass
+    cudaEvent_t ev_rho = nullptr, ev_halo = nullptr;
     nprsph_ctx* left = nullptr;        // local transport only
     nprsph_ctx* right = nullptr;
 
