@@ -56,63 +56,93 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML (the source nvidia-smi
+    itself reads) is polled every 20 ms from a thread; `nvidia-smi -lms` is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.samples, self.marks = index, None, [], []
+        self.stop_flag = threading.Event()
+        self.source = None
+
+    def _nvml_loop(self, nv, handle, max_mhz):
+        R = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+             "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((time.time(), float(mhz), float(max_mhz),
+                                     [k for k, b in R.items() if bits & b]))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def _smi_loop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append((time.time(), float(f[0]), float(f[1]),
+                                     [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
+            except (ValueError, IndexError):
+                continue
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h, mx), daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                  "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.source = "nvidia-smi"
+            self.t = threading.Thread(target=self._smi_loop, daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
-
     def mark(self):
         """Wall-clock marker: call at the start and at the end of the timed region."""
-        self.marks = getattr(self, "marks", []) + [time.time()]
+        self.marks.append(time.time())
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        marks = getattr(self, "marks", [])
-        lines, window = self.lines, "sampler lifetime (warm-up + timed region, same workload)"
-        if len(marks) == 2:
-            inside = [x for x in self.lines if marks[0] <= x[0] <= marks[1] + 0.15]
-            if len(inside) >= 2:
-                lines, window = inside, "timed region"
-        for _, ln in lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        time.sleep(0.03)
+        samples, window = self.samples, "sampler lifetime (warm-up + timed region, same workload)"
+        if len(self.marks) == 2:
+            inside = [x for x in samples if self.marks[0] <= x[0] <= self.marks[1]]
+            if len(inside) >= 2:
+                samples, window = inside, "timed region"
+        sm = [x[1] for x in samples]
+        reasons = sorted({r for x in samples for r in x[3]})
         return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "window": window,
-                "reasons": sorted(reasons)}
+                "sm_max_mhz": max((x[2] for x in samples), default=None), "samples": len(sm),
+                "window": window, "source": self.source, "reasons": reasons}
 
 
 def dist_env():
