@@ -178,6 +178,12 @@ int nprsph_debug_read(nprsph_ctx* ctx, int item, void* host_dst, uint64_t bytes)
 int nprsph_sort_pairs_host(int device, const uint32_t* keys_in, const uint32_t* vals_in,
                            uint64_t n, int key_bits, uint32_t* keys_out, uint32_t* vals_out);
 
+/* ---- snapshots (new: the reference's state never leaves the GPU) ------------ */
+/* file = 256-byte header (parameters, n, step count), the slot table of the cell-ordered
+ * arrangement and n 64-byte records in original order; a loaded run continues bit for bit */
+int nprsph_snapshot_save(nprsph_ctx* ctx, const char* path);
+int nprsph_snapshot_load(nprsph_ctx* ctx, const char* path);
+
 /* ---- OpenGL presenter (VAO attr 0 on the SSBO, Main.cpp:529-535) --------------------------- */
 /* Registers the caller's GL buffer (>= n*64 B) through CUDA-GL interop; publish copies the
  * current records into it.  Need a current GL context; headless callers never call these. */

@@ -88,6 +88,8 @@ SYMBOLS = {
     "nprsph_profile_step": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "nprsph_debug_read": (C.c_int, [_P, C.c_int, _P, C.c_uint64]),
     "nprsph_sort_pairs_host": (C.c_int, [C.c_int, _P, _P, C.c_uint64, C.c_int, _P, _P]),
+    "nprsph_snapshot_save": (C.c_int, [_P, C.c_char_p]),
+    "nprsph_snapshot_load": (C.c_int, [_P, C.c_char_p]),
     "nprsph_gl_register": (C.c_int, [_P, C.c_uint]),
     "nprsph_gl_publish": (C.c_int, [_P]),
     "nprsph_gl_unregister": (C.c_int, [_P]),
@@ -300,6 +302,12 @@ class Simulation:
         s = Stats()
         self._ck(self.lib.nprsph_get_stats(self._h, C.byref(s)))
         return s
+
+    def save(self, path: str):
+        self._ck(self.lib.nprsph_snapshot_save(self._h, str(path).encode()))
+
+    def load(self, path: str):
+        self._ck(self.lib.nprsph_snapshot_load(self._h, str(path).encode()))
 
     def profile_step(self, n_steps=1) -> dict:
         ms = (C.c_float * len(STAGES))()

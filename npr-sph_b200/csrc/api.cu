@@ -5,6 +5,7 @@
 // upload (Main.cpp:274-278) and the p/r keys (Main.cpp:454-476).  Everything runs on one CUDA
 // stream; there is no CPU implementation of any pass behind this API.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -695,6 +696,124 @@ done:
     for (int b = 0; b < 2; b++) { cudaFree(k[b]); cudaFree(v[b]); }
     cudaFree(ws);
     if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+// ---- snapshots (the reference keeps its state on the GPU only) ---------------------
+// File = 256-byte header, slot_ids[n] (uint32: original index held by each slot of the cell-ordered
+// arrangement), Particle[n] (64 B records, original order).  Loading restores the arrangement as
+// well, so a restarted run continues bit for bit like the uninterrupted one.
+namespace {
+struct SnapshotHeader {
+    char magic[8];                 // "NPRSPH01"
+    uint32_t header_bytes, record_bytes;
+    uint64_t n, steps_done;
+    nprsph_constants consts;
+    nprsph_boundary bounds;
+    float particle_radius, gas_const, gravity[3], damping, dt, pi;
+    int32_t cell_subdiv, paused;
+};
+static_assert(sizeof(SnapshotHeader) <= 256, "snapshot header must fit 256 bytes");
+}
+
+int nprsph_snapshot_save(nprsph_ctx* c, const char* path) {
+    GUARD(c);
+    if (!path) return NPRSPH_ERR_INVALID;
+    if (c->dist) return fail(c, NPRSPH_ERR_STATE, "snapshots of a slab-decomposed run are per rank: use nprsph_dist_download%s");
+    int rc = publish(c);
+    if (rc) return rc;
+    const uint64_t n = c->n;
+    nprsph_particle* rec = (nprsph_particle*)malloc((n ? n : 1) * sizeof(nprsph_particle));
+    uint32_t* ids = (uint32_t*)malloc((n ? n : 1) * sizeof(uint32_t));
+    uint32_t* d_ids = nullptr;
+    FILE* f = nullptr;
+    rc = NPRSPH_OK;
+    if (!rec || !ids) { rc = fail(c, NPRSPH_ERR_NOMEM, "out of host memory%s"); goto done; }
+    if (n) {
+        cudaError_t e = cudaMalloc(&d_ids, n * 4);
+        if (e == cudaSuccess) { launch_slot_ids(c->pos[c->cur], d_ids, (uint32_t)n, c->stream); e = cudaGetLastError(); }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ids, d_ids, n * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(rec, c->aos, n * sizeof(nprsph_particle), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = fail(c, NPRSPH_ERR_CUDA, "snapshot_save: %s", cudaGetErrorString(e)); goto done; }
+    }
+    {
+        unsigned char raw[256];
+        memset(raw, 0, sizeof raw);
+        SnapshotHeader h;
+        memset(&h, 0, sizeof h);
+        memcpy(h.magic, "NPRSPH01", 8);
+        h.header_bytes = 256; h.record_bytes = sizeof(nprsph_particle);
+        h.n = n; h.steps_done = c->steps_done;
+        h.consts = c->consts; h.bounds = c->bounds;
+        h.particle_radius = c->cfg.particle_radius; h.gas_const = c->cfg.gas_const;
+        for (int a = 0; a < 3; a++) h.gravity[a] = c->cfg.gravity[a];
+        h.damping = c->cfg.damping; h.dt = c->cfg.dt; h.pi = c->cfg.pi;
+        h.cell_subdiv = c->cfg.cell_subdiv; h.paused = c->paused ? 1 : 0;
+        memcpy(raw, &h, sizeof h);
+        f = fopen(path, "wb");
+        if (!f || fwrite(raw, 1, 256, f) != 256 || fwrite(ids, 4, n, f) != n ||
+            fwrite(rec, sizeof(nprsph_particle), n, f) != n)
+            rc = fail(c, NPRSPH_ERR_INVALID, "cannot write snapshot %s", path);
+    }
+done:
+    if (f) fclose(f);
+    free(rec); free(ids);
+    if (d_ids) cudaFree(d_ids);
+    return rc;
+}
+
+int nprsph_snapshot_load(nprsph_ctx* c, const char* path) {
+    GUARD(c);
+    if (!path) return NPRSPH_ERR_INVALID;
+    if (c->dist) return fail(c, NPRSPH_ERR_STATE, "not available in slab mode%s");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(c, NPRSPH_ERR_INVALID, "cannot open snapshot %s", path);
+    unsigned char raw[256];
+    SnapshotHeader h;
+    nprsph_particle* rec = nullptr;
+    uint32_t* ids = nullptr;
+    uint32_t* d_ids = nullptr;
+    int rc = NPRSPH_OK;
+    if (fread(raw, 1, 256, f) != 256) { rc = fail(c, NPRSPH_ERR_INVALID, "truncated snapshot %s", path); goto done; }
+    memcpy(&h, raw, sizeof h);
+    if (memcmp(h.magic, "NPRSPH01", 8) != 0 || h.header_bytes != 256 || h.record_bytes != sizeof(nprsph_particle) ||
+        h.n >= (1ull << 30)) { rc = fail(c, NPRSPH_ERR_INVALID, "not an NPRSPH01 snapshot: %s", path); goto done; }
+    rec = (nprsph_particle*)malloc((h.n ? h.n : 1) * sizeof(nprsph_particle));
+    ids = (uint32_t*)malloc((h.n ? h.n : 1) * sizeof(uint32_t));
+    if (!rec || !ids) { rc = fail(c, NPRSPH_ERR_NOMEM, "out of host memory%s"); goto done; }
+    if (fread(ids, 4, h.n, f) != h.n || fread(rec, sizeof(nprsph_particle), h.n, f) != h.n) {
+        rc = fail(c, NPRSPH_ERR_INVALID, "truncated snapshot %s", path); goto done;
+    }
+    for (uint64_t s = 0; s < h.n; s++)
+        if (ids[s] >= h.n) { rc = fail(c, NPRSPH_ERR_INVALID, "corrupt slot table in %s", path); goto done; }
+    c->consts = h.consts; c->bounds = h.bounds;
+    c->cfg.particle_radius = h.particle_radius; c->cfg.gas_const = h.gas_const;
+    for (int a = 0; a < 3; a++) c->cfg.gravity[a] = h.gravity[a];
+    c->cfg.damping = h.damping; c->cfg.dt = h.dt; c->cfg.pi = h.pi;
+    if (h.cell_subdiv >= 1 && h.cell_subdiv <= 4) c->cfg.cell_subdiv = h.cell_subdiv;
+    c->paused = h.paused != 0;
+    c->params_dirty = true;
+    rc = nprsph_upload_particles(c, rec, h.n);        // original order: AoS view + SoA with ids
+    if (rc) goto done;
+    if (h.n) {                                         // re-establish the saved cell order
+        const int nxt = 1 - c->cur;
+        cudaError_t e = cudaMalloc(&d_ids, h.n * 4);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ids, ids, h.n * 4, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+            launch_gather(d_ids, c->pos[c->cur], c->vel[c->cur], c->frc[c->cur], c->pos[nxt], c->vel[nxt],
+                          c->frc[nxt], (uint32_t)h.n, c->stream);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = fail(c, NPRSPH_ERR_CUDA, "snapshot_load: %s", cudaGetErrorString(e)); goto done; }
+        c->cur = nxt;
+    }
+    c->steps_done = h.steps_done;
+done:
+    fclose(f);
+    free(rec); free(ids);
+    if (d_ids) cudaFree(d_ids);
     return rc;
 }
 

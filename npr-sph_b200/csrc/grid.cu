@@ -115,6 +115,20 @@ k_fill_gaps(const uint4* __restrict__ gap_list, const uint32_t* __restrict__ gap
     }
 }
 
+// plain gather of the three SoA arrays by a slot permutation (snapshot restore)
+__global__ void __launch_bounds__(TPB)
+k_gather(const uint32_t* __restrict__ src_of_slot, const float4* __restrict__ pos_in,
+         const float4* __restrict__ vel_in, const float4* __restrict__ frc_in,
+         float4* __restrict__ pos_out, float4* __restrict__ vel_out, float4* __restrict__ frc_out,
+         uint32_t n) {
+    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t src = src_of_slot[s];
+    pos_out[s] = pos_in[src];
+    vel_out[s] = vel_in[src];
+    frc_out[s] = frc_in[src];
+}
+
 __global__ void __launch_bounds__(TPB)
 k_count_nan(const float4* __restrict__ posid, uint32_t n, unsigned long long* __restrict__ out) {
     const uint32_t i = blockIdx.x * TPB + threadIdx.x;
@@ -171,6 +185,12 @@ void launch_reorder_cells(const uint32_t* sorted_keys, const uint32_t* perm, con
 void launch_fill_gaps(const uint4* gap_list, const uint32_t* gap_count, uint32_t* cell_start,
                       int num_sms, cudaStream_t st) {
     k_fill_gaps<<<num_sms * 4, TPB, 0, st>>>(gap_list, gap_count, cell_start);
+}
+
+void launch_gather(const uint32_t* src_of_slot, const float4* pos_in, const float4* vel_in,
+                   const float4* frc_in, float4* pos_out, float4* vel_out, float4* frc_out, uint32_t n,
+                   cudaStream_t st) {
+    if (n) k_gather<<<blocks_for(n, TPB), TPB, 0, st>>>(src_of_slot, pos_in, vel_in, frc_in, pos_out, vel_out, frc_out, n);
 }
 
 void launch_count_nan(const float4* posid, uint32_t n, unsigned long long* out, cudaStream_t st) {

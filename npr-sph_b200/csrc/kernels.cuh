@@ -21,6 +21,9 @@ void launch_reorder_cells(const uint32_t* sorted_keys, const uint32_t* perm, con
                           bool with_force, int num_sms, cudaStream_t st);
 void launch_fill_gaps(const uint4* gap_list, const uint32_t* gap_count, uint32_t* cell_start,
                       int num_sms, cudaStream_t st);
+void launch_gather(const uint32_t* src_of_slot, const float4* pos_in, const float4* vel_in,
+                   const float4* frc_in, float4* pos_out, float4* vel_out, float4* frc_out, uint32_t n,
+                   cudaStream_t st);
 void launch_count_nan(const float4* posid, uint32_t n, unsigned long long* out, cudaStream_t st);
 void launch_slot_ids(const float4* posid, uint32_t* ids, uint32_t n, cudaStream_t st);
 

@@ -162,3 +162,32 @@ def test_dense_clump_overflows_the_hitmask_gracefully(sph, oracle):
     cf = oracle.pass_force(P, p, counts=True)
     assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_RHO), c)
     assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_FORCE), cf)
+
+
+def test_snapshot_restart_is_bit_exact(sph, oracle, tmp_path):
+    """save -> load restores parameters, records and the cell-ordered
+    arrangement, so the restarted run continues bit for bit."""
+    nx = 20
+    p = oracle.dam_break_params(nx, nx, nx)
+    a = sph.Simulation(cell_subdiv=2)
+    a.apply_params(p)
+    a.scene_block(nx, nx, nx, 0.005, None, 2e-4, 5)
+    a.set_paused(False)
+    a.step(7)
+    path = tmp_path / "snap.nprsph"
+    a.save(path)
+    assert path.stat().st_size == 256 + nx ** 3 * (4 + 64)
+    a.step(5)
+    A = a.download()
+    b = sph.Simulation(cell_subdiv=1)                 # different settings: the file must override them
+    b.load(path)
+    assert not b.paused and b.num_particles == nx ** 3 and b.stats().steps_done == 7
+    assert b.get_constants().mass == pytest.approx(p.mass) and b.stats().cell_subdiv == 2
+    b.step(5)
+    B = b.download()
+    assert np.array_equal(A.view(np.uint32), B.view(np.uint32))
+    with pytest.raises(sph.NprSphError):
+        b.load(tmp_path / "missing.nprsph")
+    (tmp_path / "junk").write_bytes(b"x" * 300)
+    with pytest.raises(sph.NprSphError):
+        b.load(tmp_path / "junk")
