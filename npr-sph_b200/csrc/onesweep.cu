@@ -1,14 +1,16 @@
 // onesweep.cu -- hand-written least-significant-digit radix sort of (cell key, slot) pairs.
 //
-// One histogram kernel reads the keys once and counts every 8-bit digit position; then one
-// "onesweep" kernel per digit moves the pairs: each CTA takes a tile of 4096 pairs (dynamic
-// tile ticket, so every predecessor tile is already resident), ranks its keys stably with
-// warp match-any, publishes its per-digit counts to a tile-status array and resolves its
-// global offsets by decoupled look-back over the predecessors' status words (count and flag
-// share one 32-bit word, so no fence is needed).  Pairs are staged through shared memory so
-// the global scatter is written in digit-contiguous runs.
+// One histogram kernel reads the keys once and counts every digit position; then one "onesweep"
+// kernel per digit moves the pairs: each CTA takes a tile of 4096 pairs (dynamic tile ticket, so
+// every predecessor tile is already resident), ranks its keys stably inside each warp,
+// publishes its per-digit counts to a tile-status array and resolves its global offsets by
+// decoupled look-back over the predecessors' status words (count and flag share one 32-bit word,
+// so no fence is needed).  Pairs are staged through shared memory so the global scatter is
+// written in digit-contiguous runs.
 //
-// Only the low `key_bits` bits are sorted (ceil(log2(num_cells+1)) for cell keys).
+// Only the low `key_bits` bits are sorted (ceil(log2(num_cells+1)) for cell keys).  Digits are
+// 8 bits wide, or 9 bits when that saves a whole pass (27-bit keys of the 16 Mi-particle grid:
+// 3 passes instead of 4).
 // No reference counterpart: the reference searches neighbours all-pairs
 // (rho_pres_comp.glsl:46, force_comp.glsl:48).
 #include "sort.cuh"
@@ -22,6 +24,12 @@ constexpr uint32_t FLAG_INCL = 1u << 31;   // inclusive prefix published
 constexpr uint32_t FLAG_ANY  = FLAG_AGG | FLAG_INCL;
 constexpr uint32_t VALUE_MASK = FLAG_AGG - 1;
 
+struct DigitPlan {                 // digit position of every pass
+    int passes;
+    int shift[SORT_MAX_PASSES];
+    uint32_t mask[SORT_MAX_PASSES];
+};
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // ---- digit histograms for all passes in one read of the keys --------------------------------
@@ -32,10 +40,9 @@ constexpr int HIST_THREADS = 256;
 constexpr int HIST_ITEMS = 16;
 
 __global__ void __launch_bounds__(HIST_THREADS)
-k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int passes, int key_bits,
-             uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sh[SORT_MAX_PASSES][RADIX];
-    for (int i = threadIdx.x; i < SORT_MAX_PASSES * RADIX; i += HIST_THREADS) (&sh[0][0])[i] = 0;
+k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, DigitPlan plan, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[SORT_MAX_PASSES][SORT_MAX_RADIX];
+    for (int i = threadIdx.x; i < SORT_MAX_PASSES * SORT_MAX_RADIX; i += HIST_THREADS) (&sh[0][0])[i] = 0;
     __syncthreads();
 
     const uint64_t chunk = (uint64_t)HIST_THREADS * HIST_ITEMS;
@@ -56,10 +63,9 @@ k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int passes, int key_
             for (int v = 0; v < HIST_ITEMS; v++)
                 if (first + v < n) { k[v] = keys[first + v]; cnt = v + 1; }
         }
-        for (int p = 0; p < passes; p++) {
-            const int shift = p * RADIX_BITS;
-            const int bits = key_bits - shift;
-            const uint32_t mask = bits >= RADIX_BITS ? (uint32_t)(RADIX - 1) : ((1u << bits) - 1u);
+        for (int p = 0; p < plan.passes; p++) {
+            const int shift = plan.shift[p];
+            const uint32_t mask = plan.mask[p];
             uint32_t run_d = cnt ? ((k[0] >> shift) & mask) : 0xFFFFFFFFu;
             uint32_t run = cnt ? 1u : 0u;
 #pragma unroll
@@ -82,7 +88,7 @@ k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int passes, int key_
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < passes * RADIX; i += HIST_THREADS) {
+    for (int i = threadIdx.x; i < plan.passes * SORT_MAX_RADIX; i += HIST_THREADS) {
         const uint32_t c = (&sh[0][0])[i];
         if (c) atomicAdd(hist + i, c);
     }
@@ -108,23 +114,31 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
 }
 
 // ---- one digit pass ---------------------------------------------------------------------------
-template <bool IOTA>
+// BITS: digit width the kernel is built for (radix 2^BITS, DPT = radix/256 digits per thread in the
+// scan / look-back phase); the pass may use fewer bits (mask).
+template <int BITS, bool IOTA>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
            uint32_t mask, const uint32_t* __restrict__ hist, uint32_t* __restrict__ tile_counter,
            volatile uint32_t* __restrict__ status) {
-    __shared__ uint32_t s_keys[SORT_TILE];
-    __shared__ uint32_t s_vals[SORT_TILE];
-    __shared__ uint32_t s_warp_hist[SORT_WARPS][RADIX];
-    __shared__ uint32_t s_out_base[RADIX];    // global position of local slot 0 of each digit run
-    __shared__ uint32_t s_local_off[RADIX];
+    constexpr int RDX = 1 << BITS;
+    constexpr int DPT = RDX / SORT_THREADS;
+    static_assert(SORT_WARPS * RDX <= SORT_TILE, "warp histograms must fit the value staging area");
+    // [0, TILE): staged keys.  [TILE, 2*TILE): the per-warp digit counters while ranking, then the
+    // staged values (every read of the counters is finished before the first value is staged).
+    __shared__ uint32_t s_buf[2 * SORT_TILE];
+    __shared__ uint32_t s_out_base[RDX];      // global position of local slot 0 of each digit run
+    __shared__ uint32_t s_local_off[RDX];
     __shared__ uint32_t s_scan[SORT_WARPS];
     __shared__ uint32_t s_tile;
+    uint32_t* s_keys = s_buf;
+    uint32_t* s_vals = s_buf + SORT_TILE;
+    uint32_t* s_warp_hist = s_buf + SORT_TILE;              // [SORT_WARPS][RDX]
 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
+    for (int i = tid; i < SORT_WARPS * RDX; i += SORT_THREADS) s_warp_hist[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t tile_base = tile * SORT_TILE;
@@ -138,25 +152,21 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
         key[k] = (idx < n) ? keys_in[idx] : 0xFFFFFFFFu;
     }
 
-    // stable rank of every key among the keys of its warp with the same digit
-    // All match-any votes are issued first (independent), then one shared-memory atomic per
-    // distinct digit per row (by the lowest peer lane) claims the rank base, which is broadcast
-    // back with a shuffle.  Atomics of one warp to one address retire in program order, so row k
-    // ranks below row k+1: the sort stays stable, and the 16 rows overlap instead of forming one
-    // load -> store dependency chain.
+    // Stable rank of every key among the keys of its warp with the same digit.  The votes of all
+    // rows are issued first (independent); then one shared-memory atomic per distinct digit per
+    // row (by the lowest peer lane) claims the rank base, broadcast back with a shuffle.  Atomics
+    // of one warp to one address retire in program order, so row k ranks below row k+1: the sort
+    // stays stable, and the 16 rows overlap instead of forming one load -> store chain.
     uint32_t rank[SORT_ITEMS];
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t* my_hist = s_warp_hist[warp];
-    // Cell-ordered keys share their upper digits over long runs: when a whole row of 32 keys has
-    // one digit (two REDUX votes), the match-any vote -- the slowest instruction of the kernel --
-    // is skipped.
+    uint32_t* my_hist = s_warp_hist + warp * RDX;
     uint32_t peers[SORT_ITEMS];
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; k++) {
         // MATCH.ANY costs one round per distinct value in the warp.  Cell-ordered keys give rows
         // whose digits are either all equal or count upwards (consecutive cells; after the first
-        // pass, keys 256 apart), i.e. all distinct: both cases are recognised with two shuffles
-        // and a vote, and only irregular rows pay for the match.
+        // pass, keys one radix apart), i.e. all distinct: both cases are recognised with two
+        // shuffles and a vote, and only irregular rows pay for the match.
         const uint32_t d = (key[k] >> shift) & mask;
         const uint32_t e = (d - __shfl_sync(0xffffffffu, d, 0)) & mask;     // offset from lane 0, cyclic
         const uint32_t below_e = __shfl_up_sync(0xffffffffu, e, 1);
@@ -176,45 +186,78 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     }
     __syncthreads();
 
-    // thread d owns digit d: counts across warps -> exclusive warp offsets + tile count
-    const uint32_t d_own = tid;
-    uint32_t tile_count = 0;
+    // thread t owns digits t*DPT .. t*DPT+DPT-1: counts across warps -> exclusive warp offsets + tile count
+    uint32_t tile_count[DPT], hist_own[DPT];
+    uint32_t sum_tc = 0, sum_h = 0;
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) {
-        const uint32_t c = s_warp_hist[w][d_own];
-        s_warp_hist[w][d_own] = tile_count;
-        tile_count += c;
-    }
-    status[(uint64_t)tile * RADIX + d_own] = tile_count | (tile == 0 ? FLAG_INCL : FLAG_AGG);
-
-    const uint32_t global_excl = block_excl_scan_256(hist[d_own], s_scan);
-    const uint32_t local_off = block_excl_scan_256(tile_count, s_scan);
-
-    // decoupled look-back over predecessor tiles for this digit
-    uint32_t excl = 0;
-    if (tile > 0) {
-        int64_t t = (int64_t)tile - 1;
-        while (true) {
-            const uint32_t v = status[(uint64_t)t * RADIX + d_own];
-            if ((v & FLAG_ANY) == 0) continue;            // predecessor not published yet: spin
-            excl += v & VALUE_MASK;
-            if (v & FLAG_INCL) break;
-            t--;
+    for (int q = 0; q < DPT; q++) {
+        const uint32_t d_own = tid * DPT + q;
+        uint32_t tc = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            const uint32_t c = s_warp_hist[w * RDX + d_own];
+            s_warp_hist[w * RDX + d_own] = tc;
+            tc += c;
         }
-        status[(uint64_t)tile * RADIX + d_own] = ((excl + tile_count) & VALUE_MASK) | FLAG_INCL;
+        tile_count[q] = tc;
+        status[(uint64_t)tile * RDX + d_own] = tc | (tile == 0 ? FLAG_INCL : FLAG_AGG);
+        hist_own[q] = hist[d_own];
+        sum_tc += tc; sum_h += hist_own[q];
     }
-    s_out_base[d_own] = global_excl + excl - local_off;
-    s_local_off[d_own] = local_off;
+    uint32_t global_excl = block_excl_scan_256(sum_h, s_scan);
+    uint32_t local_off = block_excl_scan_256(sum_tc, s_scan);
+
+    // decoupled look-back over predecessor tiles, the DPT digits of a thread interleaved
+    uint32_t excl[DPT];
+    if (tile > 0) {
+        int64_t t[DPT];
+        bool done[DPT];
+#pragma unroll
+        for (int q = 0; q < DPT; q++) { excl[q] = 0; t[q] = (int64_t)tile - 1; done[q] = false; }
+        bool all_done = false;
+        while (!all_done) {
+            all_done = true;
+#pragma unroll
+            for (int q = 0; q < DPT; q++) {
+                if (done[q]) continue;
+                const uint32_t v = status[(uint64_t)t[q] * RDX + tid * DPT + q];
+                if (v & FLAG_ANY) {                       // else: predecessor not published yet, spin
+                    excl[q] += v & VALUE_MASK;
+                    if (v & FLAG_INCL) done[q] = true; else t[q]--;
+                }
+                all_done = all_done && done[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < DPT; q++)
+            status[(uint64_t)tile * RDX + tid * DPT + q] = ((excl[q] + tile_count[q]) & VALUE_MASK) | FLAG_INCL;
+    } else {
+#pragma unroll
+        for (int q = 0; q < DPT; q++) excl[q] = 0;
+    }
+#pragma unroll
+    for (int q = 0; q < DPT; q++) {
+        const uint32_t d_own = tid * DPT + q;
+        s_out_base[d_own] = global_excl + excl[q] - local_off;
+        s_local_off[d_own] = local_off;
+        global_excl += hist_own[q];
+        local_off += tile_count[q];
+    }
     __syncthreads();
 
-    // stage pairs in tile-sorted order
+    // final position of every pair inside the tile (last reads of the warp counters) ...
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; k++) {
         const uint32_t d = (key[k] >> shift) & mask;
-        const uint32_t p = s_local_off[d] + my_hist[d] + rank[k];
+        rank[k] += s_local_off[d] + my_hist[d];
+    }
+    __syncthreads();
+    // ... then stage the pairs in tile-sorted order (values overwrite the counters)
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
         const uint32_t idx = warp_base + k * 32 + lane;
-        s_keys[p] = key[k];
-        s_vals[p] = IOTA ? idx : ((idx < n) ? vals_in[idx] : 0u);
+        s_keys[rank[k]] = key[k];
+        s_vals[rank[k]] = IOTA ? idx : ((idx < n) ? vals_in[idx] : 0u);
     }
     __syncthreads();
 
@@ -232,22 +275,39 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     }
 }
 
+DigitPlan make_plan(int key_bits, int* digit_bits) {
+    const int p8 = (key_bits + 7) / 8, p9 = (key_bits + 8) / 9;
+    const int width = (p9 < p8) ? 9 : 8;
+    DigitPlan plan;
+    plan.passes = (key_bits + width - 1) / width;
+    for (int p = 0; p < SORT_MAX_PASSES; p++) {
+        int bits = key_bits - p * width;
+        if (bits > width) bits = width;
+        if (bits < 1) bits = 1;
+        plan.shift[p] = p * width;
+        plan.mask[p] = (1u << bits) - 1u;
+    }
+    *digit_bits = width;
+    return plan;
+}
+
 }  // namespace
 
 size_t sort_workspace_bytes(uint64_t n) {
     const uint64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
-    // [passes][256] histograms, [passes] tile tickets (padded), [passes][tiles][256] status
-    return sizeof(uint32_t) * (SORT_MAX_PASSES * RADIX + 64 + SORT_MAX_PASSES * tiles * RADIX);
+    // [passes][radix] histograms, [passes] tile tickets (padded), [passes][tiles][radix] status
+    return sizeof(uint32_t) * (SORT_MAX_PASSES * SORT_MAX_RADIX + 64 + SORT_MAX_PASSES * tiles * SORT_MAX_RADIX);
 }
 
 int sort_num_passes(int key_bits) {
     if (key_bits < 1) key_bits = 1;
     if (key_bits > 32) key_bits = 32;
-    return (key_bits + RADIX_BITS - 1) / RADIX_BITS;
+    int width;
+    return make_plan(key_bits, &width).passes;
 }
 
-// Sorts (keys_a, iota) by the low key_bits bits.  Buffers ping-pong a -> b -> a ...; returns in
-// *result_in_b whether the sorted pairs ended in the b buffers.  vals_a is scratch.
+// Sorts (keys_a, vals_a or iota) by the low key_bits bits.  Buffers ping-pong a -> b -> a ...;
+// returns in *result_in_b whether the sorted pairs ended in the b buffers.
 cudaError_t sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                        uint64_t n64, int key_bits, bool iota_vals, void* workspace,
                        int num_sms, cudaStream_t stream, bool* result_in_b) {
@@ -257,38 +317,39 @@ cudaError_t sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uin
     const uint32_t n = (uint32_t)n64;
     if (key_bits < 1) key_bits = 1;
     if (key_bits > 32) key_bits = 32;
-    const int passes = sort_num_passes(key_bits);
+    int width;
+    const DigitPlan plan = make_plan(key_bits, &width);
+    const uint32_t radix = 1u << width;
     const uint32_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
-    uint32_t* hist = static_cast<uint32_t*>(workspace);
-    uint32_t* tickets = hist + SORT_MAX_PASSES * RADIX;
+    uint32_t* hist = static_cast<uint32_t*>(workspace);          // [pass][SORT_MAX_RADIX]
+    uint32_t* tickets = hist + SORT_MAX_PASSES * SORT_MAX_RADIX;
     uint32_t* status = tickets + 64;
 
     cudaError_t e = cudaMemsetAsync(workspace, 0,
-        sizeof(uint32_t) * (SORT_MAX_PASSES * RADIX + 64 + (size_t)passes * tiles * RADIX), stream);
+        sizeof(uint32_t) * (SORT_MAX_PASSES * SORT_MAX_RADIX + 64 + (size_t)plan.passes * tiles * radix), stream);
     if (e != cudaSuccess) return e;
 
     const uint64_t chunk = (uint64_t)HIST_THREADS * HIST_ITEMS;
     uint32_t hist_blocks = (uint32_t)((n + chunk - 1) / chunk);
     const uint32_t max_blocks = (uint32_t)num_sms * 8;
     if (hist_blocks > max_blocks) hist_blocks = max_blocks;
-    k_radix_hist<<<hist_blocks, HIST_THREADS, 0, stream>>>(keys_a, n, passes, key_bits, hist);
+    k_radix_hist<<<hist_blocks, HIST_THREADS, 0, stream>>>(keys_a, n, plan, hist);
 
     uint32_t* kin = keys_a; uint32_t* vin = vals_a; uint32_t* kout = keys_b; uint32_t* vout = vals_b;
-    for (int p = 0; p < passes; p++) {
-        const int shift = p * RADIX_BITS;
-        int bits = key_bits - shift; if (bits > RADIX_BITS) bits = RADIX_BITS;
-        const uint32_t mask = (1u << bits) - 1u;
-        if (p == 0 && iota_vals)
-            k_onesweep<true><<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n, shift, mask,
-                hist + p * RADIX, tickets + p, status + (size_t)p * tiles * RADIX);
-        else
-            k_onesweep<false><<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n, shift, mask,
-                hist + p * RADIX, tickets + p, status + (size_t)p * tiles * RADIX);
+    for (int p = 0; p < plan.passes; p++) {
+        const uint32_t* h = hist + p * SORT_MAX_RADIX;
+        uint32_t* ticket = tickets + p;
+        uint32_t* st = status + (size_t)p * tiles * radix;
+        const bool iota = (p == 0 && iota_vals);
+#define LAUNCH(B, I) k_onesweep<B, I><<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n, plan.shift[p], plan.mask[p], h, ticket, st)
+        if (width == 9) { if (iota) LAUNCH(9, true); else LAUNCH(9, false); }
+        else            { if (iota) LAUNCH(8, true); else LAUNCH(8, false); }
+#undef LAUNCH
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
-    *result_in_b = (passes & 1) != 0;
+    *result_in_b = (plan.passes & 1) != 0;
     return cudaGetLastError();
 }
 

@@ -6,8 +6,7 @@
 
 namespace nprsph {
 
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_MAX_RADIX = 512;                    // 8-bit digits, or 9-bit when that saves a pass
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
