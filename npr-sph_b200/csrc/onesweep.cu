@@ -208,29 +208,35 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     uint32_t local_off = block_excl_scan_256(sum_tc, s_scan);
 
     // decoupled look-back over predecessor tiles, the DPT digits of a thread interleaved
+    // Each step reads a window of LOOK predecessors at once: the loads are independent, so a walk
+    // of depth k costs ceil(k / LOOK) L2 round trips instead of k (the walk was a third of the
+    // kernel's stall samples when it read one status word at a time).
+    constexpr int LOOK = 8;
     uint32_t excl[DPT];
     if (tile > 0) {
-        int64_t t[DPT];
-        bool done[DPT];
 #pragma unroll
-        for (int q = 0; q < DPT; q++) { excl[q] = 0; t[q] = (int64_t)tile - 1; done[q] = false; }
-        bool all_done = false;
-        while (!all_done) {
-            all_done = true;
+        for (int q = 0; q < DPT; q++) {
+            const uint32_t d_own = tid * DPT + q;
+            uint32_t acc = 0;
+            int64_t t = (int64_t)tile - 1;               // next predecessor to consume
+            bool done = false;
+            while (!done) {
+                uint32_t v[LOOK];
 #pragma unroll
-            for (int q = 0; q < DPT; q++) {
-                if (done[q]) continue;
-                const uint32_t v = status[(uint64_t)t[q] * RDX + tid * DPT + q];
-                if (v & FLAG_ANY) {                       // else: predecessor not published yet, spin
-                    excl[q] += v & VALUE_MASK;
-                    if (v & FLAG_INCL) done[q] = true; else t[q]--;
+                for (int w = 0; w < LOOK; w++)
+                    v[w] = (t - w >= 0) ? status[(uint64_t)(t - w) * RDX + d_own] : (uint32_t)(1u << 31);   // before tile 0: inclusive prefix 0
+#pragma unroll
+                for (int w = 0; w < LOOK; w++) {
+                    if (done) break;
+                    if ((v[w] & FLAG_ANY) == 0) break;   // not published yet: poll again from here
+                    acc += v[w] & VALUE_MASK;
+                    t--;
+                    if (v[w] & FLAG_INCL) done = true;
                 }
-                all_done = all_done && done[q];
             }
+            excl[q] = acc;
+            status[(uint64_t)tile * RDX + d_own] = ((acc + tile_count[q]) & VALUE_MASK) | FLAG_INCL;
         }
-#pragma unroll
-        for (int q = 0; q < DPT; q++)
-            status[(uint64_t)tile * RDX + tid * DPT + q] = ((excl[q] + tile_count[q]) & VALUE_MASK) | FLAG_INCL;
     } else {
 #pragma unroll
         for (int q = 0; q < DPT; q++) excl[q] = 0;
