@@ -447,6 +447,7 @@ int nprsph_get_config(const nprsph_ctx* c, nprsph_config* cfg) {
 int nprsph_scene_block(nprsph_ctx* c, int nx, int ny, int nz, float spacing, const float origin[3],
                        float jitter, uint32_t seed) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (nx < 0 || ny < 0 || nz < 0) return fail(c, NPRSPH_ERR_INVALID, "negative block size%s");
     c->scene.nx = nx; c->scene.ny = ny; c->scene.nz = nz;
     c->scene.spacing = spacing;
@@ -458,6 +459,7 @@ int nprsph_scene_block(nprsph_ctx* c, int nx, int ny, int nz, float spacing, con
 
 int nprsph_upload_particles(nprsph_ctx* c, const nprsph_particle* host, uint64_t n) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (n && !host) return fail(c, NPRSPH_ERR_INVALID, "null host buffer%s");
     int rc = ensure_capacity(c, n);
     if (rc) return rc;
@@ -468,6 +470,7 @@ int nprsph_upload_particles(nprsph_ctx* c, const nprsph_particle* host, uint64_t
 
 int nprsph_download_particles(nprsph_ctx* c, nprsph_particle* host, uint64_t n) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (n > c->n) return fail(c, NPRSPH_ERR_INVALID, "download larger than the particle buffer%s");
     if (n && !host) return fail(c, NPRSPH_ERR_INVALID, "null host buffer%s");
     int rc = publish(c);
@@ -479,6 +482,7 @@ int nprsph_download_particles(nprsph_ctx* c, nprsph_particle* host, uint64_t n) 
 
 int nprsph_device_particles(nprsph_ctx* c, void** device_ptr, uint64_t* n) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (!device_ptr) return NPRSPH_ERR_INVALID;
     int rc = publish(c);
     if (rc) return rc;
@@ -504,6 +508,7 @@ int nprsph_is_paused(const nprsph_ctx* c) { return c ? (c->paused ? 1 : 0) : NPR
 
 int nprsph_reset(nprsph_ctx* c) {                  // 'r', Main.cpp:460-464
     GUARD(c);
+    SINGLE_ONLY(c);
     return build_scene(c);                         // pause flag and constants untouched
 }
 
@@ -520,6 +525,7 @@ static int step_once(nprsph_ctx* c) {
 
 int nprsph_step(nprsph_ctx* c, int n_steps) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (n_steps < 0) return fail(c, NPRSPH_ERR_INVALID, "negative step count%s");
     if (c->paused || c->n == 0) return NPRSPH_OK;  // if (simulate) ..., Main.cpp:293
     for (int s = 0; s < n_steps; s++) {
@@ -538,6 +544,7 @@ int nprsph_sync(nprsph_ctx* c) {
 
 int nprsph_pass_rho(nprsph_ctx* c) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (c->n == 0) return NPRSPH_OK;
     int rc = ensure_grid(c, true, nullptr);
     if (rc) return rc;
@@ -548,6 +555,7 @@ int nprsph_pass_rho(nprsph_ctx* c) {
 
 int nprsph_pass_force(nprsph_ctx* c) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (c->n == 0) return NPRSPH_OK;
     int rc = ensure_grid(c, true, nullptr);
     if (rc) return rc;
@@ -558,6 +566,7 @@ int nprsph_pass_force(nprsph_ctx* c) {
 
 int nprsph_pass_integrate(nprsph_ctx* c) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (c->n == 0) return NPRSPH_OK;
     int rc = refresh_params(c);
     if (rc) return rc;
@@ -596,6 +605,7 @@ int nprsph_get_stats(nprsph_ctx* c, nprsph_stats* out) {
 
 int nprsph_profile_step(nprsph_ctx* c, int n_steps, float* stage_ms) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (n_steps < 1 || !stage_ms) return NPRSPH_ERR_INVALID;
     cudaEvent_t ev[8];
     for (int i = 0; i < 8; i++) CK(c, cudaEventCreate(&ev[i]));
@@ -630,6 +640,7 @@ int nprsph_profile_step(nprsph_ctx* c, int n_steps, float* stage_ms) {
 
 int nprsph_debug_read(nprsph_ctx* c, int item, void* dst, uint64_t bytes) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (!dst) return NPRSPH_ERR_INVALID;
     const void* src = nullptr;
     uint64_t need = 0;
@@ -832,6 +843,7 @@ int nprsph_gl_register(nprsph_ctx* c, unsigned int gl_buffer) {
 
 int nprsph_gl_publish(nprsph_ctx* c) {
     GUARD(c);
+    SINGLE_ONLY(c);
     if (!c->gl_res) return fail(c, NPRSPH_ERR_STATE, "no GL buffer registered%s");
     int rc = publish(c);
     if (rc) return rc;

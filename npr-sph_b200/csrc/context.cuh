@@ -83,6 +83,13 @@ int fail(nprsph_ctx* c, int code, const char* fmt, const char* detail = "");
         if (e_ != cudaSuccess) return nprsph::fail((ctx), NPRSPH_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e_)); \
     } while (0)
 
+// entry points of the single-context path are not valid once the context runs in slab mode
+#define SINGLE_ONLY(ctx)                                                                  \
+    do {                                                                                  \
+        if ((ctx)->dist) return nprsph::fail((ctx), NPRSPH_ERR_STATE,                     \
+            "this context is a slab rank (nprsph_dist_init): use the nprsph_dist_* entry points%s"); \
+    } while (0)
+
 // api.cu
 int refresh_params(nprsph_ctx* c);
 template <typename T>
