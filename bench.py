@@ -319,6 +319,13 @@ def run_ours(args):
     # per-kernel device times (CUDA events between stages on the same stream), live
     prof = run.profile(max(3, min(args.steps, 10)))
     n_k = run.n_own if world == 1 else int(run.grp.info().num_own)
+    per_rank = None
+    if world > 1:                                   # every rank's stage times and slab size (skew)
+        mine = {"rank": rank, "own": n_k, "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons"),
+                **{k: round(v, 3) for k, v in prof.items() if v > 0}}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
     stage = max(ALGO_BYTES, key=lambda k: prof[k])
     peak, peak_src = peaks()
     achieved = ALGO_BYTES[stage] * n_k / (prof[stage] * 1e-3) / 1e9
@@ -336,6 +343,7 @@ def run_ours(args):
                 "per_kernel_frac": {k: round(ALGO_BYTES[k] * n_k / (prof[k] * 1e-3) / 1e9 / peak, 4)
                                     for k in ALGO_BYTES},
                 "step_frac": round(192 * n_total / world / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                "per_rank": per_rank,
                 "note": "rho/force are instruction-issue bound (DESIGN.md 4); frac is algorithmic "
                         "bytes / time / measured HBM peak, rank 0"}
 

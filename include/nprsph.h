@@ -116,7 +116,8 @@ enum {
     NPRSPH_DBG_CELL_START,      /* uint32[num_cells+2]: first slot with key >= c            */
     NPRSPH_DBG_COUNTS_RHO,      /* uint32[n] by original index; needs FLAG_COUNT_NEIGHBOURS */
     NPRSPH_DBG_COUNTS_FORCE,    /* uint32[n] by original index                              */
-    NPRSPH_DBG_LAST_PERM        /* uint32[n]: previous slot of the particle now in slot s   */
+    NPRSPH_DBG_LAST_PERM,       /* uint32[n]: previous slot of the particle now in slot s   */
+    NPRSPH_DBG_HIT_TOTALS       /* uint32[capacity]: candidates walked by the last density pass, per slot */
 };
 
 typedef struct nprsph_ctx nprsph_ctx;

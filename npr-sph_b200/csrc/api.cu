@@ -640,6 +640,12 @@ int nprsph_profile_step(nprsph_ctx* c, int n_steps, float* stage_ms) {
 
 int nprsph_debug_read(nprsph_ctx* c, int item, void* dst, uint64_t bytes) {
     GUARD(c);
+    if (item == NPRSPH_DBG_HIT_TOTALS) {           // candidates walked per slot (also in slab mode)
+        if (!dst || !c->hitmask || bytes != c->cap * 4) return fail(c, NPRSPH_ERR_INVALID, "hit totals: need cap*4 bytes and the hit bitmask%s");
+        CK(c, cudaMemcpyAsync(dst, c->hitmask + (size_t)HIT_WORDS * c->cap, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        return NPRSPH_OK;
+    }
     SINGLE_ONLY(c);
     if (!dst) return NPRSPH_ERR_INVALID;
     const void* src = nullptr;

@@ -157,6 +157,10 @@ k_classify(const uint32_t* __restrict__ keys, const float4* __restrict__ posid,
         if (mR) atomicAdd(counts + CNT_HALO_R, (uint32_t)__popc(mR));
         if (mN) atomicAdd(counts + CNT_NAN, (uint32_t)__popc(mN));
     }
+    // highest occupied x layer: the cell table only has to reach `reach` layers beyond it (the
+    // last rank of a dam break owns a long empty stretch of the box)
+    const uint32_t xm = __reduce_max_sync(0xffffffffu, cxl);
+    if (lane == 0 && xm) atomicMax(counts + CNT_XMAX, xm);
 }
 
 __global__ void __launch_bounds__(TPB)
@@ -438,6 +442,12 @@ int prepare_group(nprsph_ctx** cs, int n) {
         if (inL[r] + inR[r] > 2 * d->cap_mig || d->n_own + inL[r] + inR[r] > d->cap_own)
             return fail(c, NPRSPH_ERR_NOMEM, "own-particle capacity exceeded (raise max_own)%s");
         d->n_nan = mine[CNT_NAN];
+        {   // x layers the table must cover: occupied layers + reach; everything when the right
+            // side holds ghosts or immigrants
+            uint32_t top = mine[CNT_XMAX] + (uint32_t)d->R;
+            if (hasR || top > (uint32_t)d->lg.dim[0] - 1u) top = (uint32_t)d->lg.dim[0] - 1u;
+            d->x_top = top;
+        }
         // boundary layers after migration: stayers + the immigrants that arrive through that face
         d->hL = mine[CNT_HALO_L] + inL[r];
         d->hR = mine[CNT_HALO_R] + inR[r];
@@ -508,7 +518,7 @@ int prepare_group(nprsph_ctx** cs, int n) {
         CK(c, cudaMemsetAsync(c->gap_count, 0, sizeof(uint32_t), c->stream));
         k_cells_slab<<<blocks_for((uint64_t)lenA + lenB + 1), TPB, 0, c->stream>>>(
             d->skeys, d->own_off - d->gL, lenA, d->own_off + d->n_own, lenB, c->cell_start,
-            d->lg.num_cells + 4u, c->gap_list, c->gap_count);
+            (d->x_top + 1u) * (uint32_t)d->lg.dim[1] * (uint32_t)d->lg.dim[2] + 4u, c->gap_list, c->gap_count);
         launch_fill_gaps(c->gap_list, c->gap_count, c->cell_start, c->num_sms, c->stream);
         CK(c, cudaGetLastError());
     }

@@ -7,7 +7,7 @@ namespace nprsph {
 
 struct Migrant { float4 posid, velrho; };      // one particle changing rank (32 B)
 
-enum { CNT_LEAVE_L = 0, CNT_LEAVE_R, CNT_HALO_L, CNT_HALO_R, CNT_NAN, CNT_RESERVED, CNT_ERR_IMMIGRANT,
+enum { CNT_LEAVE_L = 0, CNT_LEAVE_R, CNT_HALO_L, CNT_HALO_R, CNT_NAN, CNT_XMAX, CNT_ERR_IMMIGRANT,
        CNT_ERR_OVERFLOW, CNT_WORDS };
 
 struct DistState {
@@ -29,6 +29,7 @@ struct DistState {
     // slot layout: [ghost L | own | ghost R]; own particles start at slot own_off
     uint32_t cap_ghost = 0, cap_own = 0, cap_mig = 0, cap_total = 0, own_off = 0;
     uint32_t n_own = 0, n_nan = 0, gL = 0, gR = 0, hL = 0, hR = 0;
+    uint32_t x_top = 0;                // highest local x cell layer any walk of this step can touch
     bool first_prepare = true;         // candidates that belong to other ranks are dropped, not sent
     uint64_t migrated_total = 0, steps_done = 0;
 
