@@ -96,6 +96,7 @@ int nprsph::refresh_params(nprsph_ctx* c) {
     s.h = c->consts.smoothing_coeff * cf.particle_radius;       // rho_pres_comp.glsl:40
     s.h2 = s.h * s.h;
     s.r2_max = r2_threshold(s.h);
+    s.one = 1.0f;
     const double h = (double)s.h, pi = (double)cf.pi, m = (double)c->consts.mass;
     s.rho_coef = (float)(m * 315.0 / (64.0 * pi * pow(h, 9.0)));            // :52
     s.pres_coef = (float)(m * 45.0 / (2.0 * pi * pow(h, 6.0)));             // force_comp.glsl:41,59

@@ -43,6 +43,9 @@ struct SphDev {
     float dt;
     float lower[3];
     float upper[3];
+    float one;          // 1.0f the compiler cannot see: fma(x, one, y) is an exactly rounded add that
+                        // ptxas cannot contract with a preceding multiply (it fuses mul.rn.f32x2 +
+                        // add.rn.f32x2 into FFMA2 even with explicit rounding modifiers)
 };
 
 __device__ __forceinline__ int cell_coord(float x, float lo, float inv_cell, int dim) {
