@@ -97,6 +97,7 @@ int nprsph::refresh_params(nprsph_ctx* c) {
     s.h2 = s.h * s.h;
     s.r2_max = r2_threshold(s.h);
     s.one = 1.0f;
+    s.zero = 0.0f;
     const double h = (double)s.h, pi = (double)cf.pi, m = (double)c->consts.mass;
     s.rho_coef = (float)(m * 315.0 / (64.0 * pi * pow(h, 9.0)));            // :52
     s.pres_coef = (float)(m * 45.0 / (2.0 * pi * pow(h, 6.0)));             // force_comp.glsl:41,59
@@ -172,7 +173,8 @@ int ensure_capacity(nprsph_ctx* c, uint64_t n) {
         CK(c, realloc_dev(c->counts_force, n));
     }
     { char* w = (char*)c->sort_ws; CK(c, realloc_dev(w, sort_workspace_bytes(n))); c->sort_ws = w; }
-    if (!(c->cfg.flags & NPRSPH_FLAG_NO_HITMASK)) CK(c, realloc_dev(c->hitmask, n * (HIT_WORDS + 1)));
+    // (column descriptors hold 27-bit slots: beyond that the force pass re-tests its candidates)
+    CK(c, realloc_dev(c->hitmask, (c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) || n > (1u << 27) ? (size_t)0 : (size_t)n * MASK_WORDS_PER_SLOT));
     c->cap = n;
     c->params_dirty = true;     // gap-list capacity depends on cap
     return NPRSPH_OK;

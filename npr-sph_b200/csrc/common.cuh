@@ -9,6 +9,10 @@ namespace nprsph {
 
 // words of neighbour-hit bits handed from the density pass to the force pass (+1 control word)
 constexpr uint32_t HIT_WORDS = 7;
+// column descriptors of a walk, stored behind the hit words (sph_passes.cu: DescWriter)
+constexpr uint32_t DESC_WORDS = 25;
+// words of the hit-mask buffer per slot of capacity
+constexpr uint32_t MASK_WORDS_PER_SLOT = HIT_WORDS + 1 + DESC_WORDS + 1;
 
 // Uniform-grid definition (DESIGN.md "Grid").  The same arithmetic is restated in
 // oracle/sph_oracle.c:oracle_grid_setup / cell_key so keys can be compared bit-exactly.
@@ -43,6 +47,7 @@ struct SphDev {
     float dt;
     float lower[3];
     float upper[3];
+    float zero;         // 0.0f the compiler cannot see (VecConsts)
     float one;          // 1.0f the compiler cannot see: fma(x, one, y) is an exactly rounded add that
                         // ptxas cannot contract with a preceding multiply (it fuses mul.rn.f32x2 +
                         // add.rn.f32x2 into FFMA2 even with explicit rounding modifiers)

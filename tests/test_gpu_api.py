@@ -130,23 +130,32 @@ def test_error_model(sph):
 
 
 def test_hitmask_and_rescan_force_paths_agree(sph, oracle):
-    """The force pass driven by the density pass's hit bitmask must give the same neighbour sets
-    (counts bit-exact) and forces as the pass that re-tests every candidate."""
+    """The force pass driven by the density pass's records (hit bitmask + column descriptors) must
+    give the same neighbour sets (counts bit-exact) and forces as the pass that re-tests every
+    candidate, on identical inputs."""
+    from conftest import assert_field_close
     nx = 24
     p = oracle.dam_break_params(nx, nx, nx)
     P = oracle.jitter(oracle.make_block(nx, nx, nx), 0.2 * 0.005, seed=3)
+    state = None
     out = []
     for flags in (sph.FLAG_COUNT_NEIGHBOURS, sph.FLAG_COUNT_NEIGHBOURS | sph.FLAG_NO_HITMASK):
         sim = sph.Simulation(cell_subdiv=2, flags=flags)
         sim.apply_params(p)
-        sim.upload(P)
-        sim.set_paused(False)
-        sim.step(4)
+        if state is None:
+            sim.upload(P)
+            sim.set_paused(False)
+            sim.step(4)
+            state = sim.download()
+        sim.upload(state)
         sim.pass_rho()
         sim.pass_force()
         out.append((sim.download(), sim.debug_read(sph.DBG_COUNTS_FORCE)))
     assert np.array_equal(out[0][1], out[1][1])
-    assert np.array_equal(out[0][0], out[1][0]), "same arithmetic in the same order: bit-identical"
+    assert np.array_equal(out[0][0][:, 12:14], out[1][0][:, 12:14]), "density/pressure: the same pass"
+    # the recorded-hit path evaluates target pairs in packed fp32x2 arithmetic: values equal to rounding
+    scale = oracle.force_scale(out[1][0].copy(), p)
+    assert_field_close(out[0][0][:, 8:11], out[1][0][:, 8:11], "force (hit records vs rescan)", scale=scale)
 
 
 def test_dense_clump_overflows_the_hitmask_gracefully(sph, oracle):
