@@ -254,3 +254,56 @@ def test_config2_one_million_vs_all_pairs(sph, oracle):
     cq = oracle.pass_rho(Q, p, counts=True, grid=1)
     cr = oracle.gpu_pass(0, R, p, counts=True)
     assert np.array_equal(cq, cr) and np.array_equal(Q.view(np.uint32), R.view(np.uint32))
+
+
+def test_config3_sixteen_million_full_size(sph, oracle):
+    """BASELINE.json configs[2] at its full size (256^3 = 16,777,216 particles, the bench
+    workload): every pass of one step against the oracle's grid-accelerated variant, which is
+    bit-identical to the all-pairs loop (checked above at 1M).  Integers exact (keys, sortedness,
+    permutation, neighbour counts incl./excl. self), fp32 fields at 1e-5 (norm gates for the
+    force: its conditioning scale is an all-pairs sum), integrate bit-exact; plus the
+    size-independent properties: counts are symmetric (an even total) and the slot ids are a
+    permutation."""
+    n1 = 256
+    p = oracle.dam_break_params(n1, n1, n1)
+    sim = make_sim(sph, p, 2)
+    sim.scene_block(n1, n1, n1, 0.005, None, 1e-4 * 0.005, 1234)
+    sim.set_paused(False)
+    sim.step(3)                                   # off the lattice, arrangement no longer the identity
+    P = sim.download()
+    n = len(P)
+    assert n == 16_777_216 and not np.isnan(P).any()
+
+    sim.upload(P)
+    sim.pass_rho()
+    g = oracle.grid_setup(p, 2)
+    keys = oracle.cell_keys(P, g)
+    ids = sim.debug_read(sph.DBG_SLOT_IDS)
+    sk = sim.debug_read(sph.DBG_SORTED_KEYS)
+    assert np.array_equal(np.bincount(ids, minlength=n), np.ones(n, np.int64)), "slot ids: a permutation"
+    assert np.array_equal(sk, keys[ids]) and np.all(sk[1:] >= sk[:-1])
+    same = sk[1:] == sk[:-1]
+    assert np.all(ids[1:][same] > ids[:-1][same]), "stable: equal keys keep their upload order"
+
+    Q = P.copy()
+    c_rho = oracle.pass_rho(Q, p, counts=True, grid=2)
+    G = sim.download()
+    assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_RHO), c_rho)
+    assert_field_close(G[:, RHO], Q[:, RHO], "rho@16M")
+    assert_field_close(G[:, PRS], Q[:, PRS], "pressure@16M",
+                       scale=p.gas_const * (np.abs(Q[:, RHO]) + p.resting_rho))
+
+    sim.upload(Q)                                 # identical inputs for the force pass
+    sim.pass_force()
+    c_f = oracle.pass_force(Q, p, counts=True, grid=2)
+    G = sim.download()
+    got = sim.debug_read(sph.DBG_COUNTS_FORCE)
+    assert np.array_equal(got, c_f)
+    assert np.array_equal(c_f + 1, c_rho), "density counts the particle itself, the force pass does not"
+    assert int(c_f.sum(dtype=np.int64)) % 2 == 0, "the neighbour relation is symmetric"
+    assert_field_close(G[:, FRC], Q[:, FRC], "force@16M", elementwise=False)
+
+    sim.upload(Q)
+    sim.pass_integrate()
+    oracle.pass_integrate(Q, p)
+    assert_bits_equal(sim.download(), Q, "integrate must be bit-exact @16M")
