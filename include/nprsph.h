@@ -81,7 +81,7 @@ typedef struct nprsph_config {
 
 #define NPRSPH_FLAG_COUNT_NEIGHBOURS 1u  /* passes also record per-particle neighbour counts */
 #define NPRSPH_FLAG_NO_HITMASK 2u        /* force pass re-tests every candidate instead of using the
-                                            density pass's hit bitmask (A/B measurements) */
+                                            density pass's column records (A/B measurements) */
 
 typedef struct nprsph_stats {
     uint64_t num_particles;
@@ -117,7 +117,7 @@ enum {
     NPRSPH_DBG_COUNTS_RHO,      /* uint32[n] by original index; needs FLAG_COUNT_NEIGHBOURS */
     NPRSPH_DBG_COUNTS_FORCE,    /* uint32[n] by original index                              */
     NPRSPH_DBG_LAST_PERM,       /* uint32[n]: previous slot of the particle now in slot s   */
-    NPRSPH_DBG_HIT_TOTALS       /* uint32[capacity]: candidates walked by the last density pass, per slot */
+    NPRSPH_DBG_RECORD_CTL       /* uint32[ceil(capacity/2)]: control word of every slot pair, last density pass */
 };
 
 typedef struct nprsph_ctx nprsph_ctx;

@@ -174,7 +174,7 @@ int ensure_capacity(nprsph_ctx* c, uint64_t n) {
     }
     { char* w = (char*)c->sort_ws; CK(c, realloc_dev(w, sort_workspace_bytes(n))); c->sort_ws = w; }
     // (column descriptors hold 27-bit slots: beyond that the force pass re-tests its candidates)
-    CK(c, realloc_dev(c->hitmask, (c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) || n > (1u << 27) ? (size_t)0 : (size_t)n * MASK_WORDS_PER_SLOT));
+    CK(c, realloc_dev(c->hitmask, (c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) || n > (1u << 27) ? (size_t)0 : rec_buffer_words(n)));
     c->cap = n;
     c->params_dirty = true;     // gap-list capacity depends on cap
     return NPRSPH_OK;
@@ -643,9 +643,10 @@ int nprsph_profile_step(nprsph_ctx* c, int n_steps, float* stage_ms) {
 
 int nprsph_debug_read(nprsph_ctx* c, int item, void* dst, uint64_t bytes) {
     GUARD(c);
-    if (item == NPRSPH_DBG_HIT_TOTALS) {           // candidates walked per slot (also in slab mode)
-        if (!dst || !c->hitmask || bytes != c->cap * 4) return fail(c, NPRSPH_ERR_INVALID, "hit totals: need cap*4 bytes and the hit bitmask%s");
-        CK(c, cudaMemcpyAsync(dst, c->hitmask + (size_t)HIT_WORDS * c->cap, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (item == NPRSPH_DBG_RECORD_CTL) {           // control word of every slot pair (also in slab mode)
+        const uint64_t half = (c->cap + 1) / 2;
+        if (!dst || !c->hitmask || bytes != half * 4) return fail(c, NPRSPH_ERR_INVALID, "record control words: need ceil(capacity/2)*4 bytes and the column records%s");
+        CK(c, cudaMemcpyAsync(dst, c->hitmask + (size_t)4 * REC_COLS * half, bytes, cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
         return NPRSPH_OK;
     }

@@ -7,12 +7,13 @@
 
 namespace nprsph {
 
-// words of neighbour-hit bits handed from the density pass to the force pass (+1 control word)
-constexpr uint32_t HIT_WORDS = 7;
-// column descriptors of a walk, stored behind the hit words (sph_passes.cu: DescWriter)
-constexpr uint32_t DESC_WORDS = 25;
-// words of the hit-mask buffer per slot of capacity
-constexpr uint32_t MASK_WORDS_PER_SLOT = HIT_WORDS + 1 + DESC_WORDS + 1;
+// Column records handed from the density pass to the force pass (sph_passes.cu "column records"):
+// one 64-bit record per non-empty column of a walk, two record planes per slot pair, one control
+// word per slot pair.
+constexpr uint32_t REC_REACH_MAX = 2;                                  // reach the records support
+constexpr uint32_t REC_COLS = (2 * REC_REACH_MAX + 1) * (2 * REC_REACH_MAX + 1);   // columns per walk
+// words of the record buffer for a capacity of n slots: 4*REC_COLS*ceil(n/2) + ceil(n/2)
+constexpr size_t rec_buffer_words(size_t n) { return (4 * (size_t)REC_COLS + 1) * ((n + 1) / 2); }
 
 // Uniform-grid definition (DESIGN.md "Grid").  The same arithmetic is restated in
 // oracle/sph_oracle.c:oracle_grid_setup / cell_key so keys can be compared bit-exactly.

@@ -39,7 +39,7 @@ struct nprsph_ctx {
     uint32_t* counts_rho = nullptr;
     uint32_t* counts_force = nullptr;
     void* sort_ws = nullptr;
-    uint32_t* hitmask = nullptr;        // [HIT_WORDS + 1][cap] neighbour-hit bits, rho -> force
+    uint32_t* hitmask = nullptr;        // column records, rho -> force (sph_passes.cu); rec_buffer_words(cap)
     bool mask_valid = false;
 
     uint32_t* cell_start = nullptr;

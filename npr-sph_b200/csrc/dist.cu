@@ -379,7 +379,7 @@ int alloc_slab(nprsph_ctx* c, uint64_t cap_own, uint64_t cap_ghost, uint64_t cap
     CK(c, realloc_dev(c->frc[1], (size_t)0));
     { char* w = (char*)c->sort_ws; CK(c, realloc_dev(w, sort_workspace_bytes(total))); c->sort_ws = w; }
     // (column descriptors hold 27-bit slots: beyond that the force pass re-tests its candidates)
-    CK(c, realloc_dev(c->hitmask, (c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) || total > (1u << 27) ? (size_t)0 : (size_t)total * MASK_WORDS_PER_SLOT));
+    CK(c, realloc_dev(c->hitmask, (c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) || total > (1u << 27) ? (size_t)0 : rec_buffer_words(total)));
     if (c->cfg.flags & NPRSPH_FLAG_COUNT_NEIGHBOURS) {
         CK(c, realloc_dev(c->counts_rho, total));
         CK(c, realloc_dev(c->counts_force, total));
