@@ -83,6 +83,9 @@ typedef struct nprsph_config {
 #define NPRSPH_FLAG_NO_HITMASK 2u        /* force pass re-tests every candidate instead of using the
                                             density pass's column records (A/B measurements) */
 
+#define NPRSPH_FLAG_NO_FUSE 4u           /* nprsph_step runs the force and integrate passes as two
+                                            launches instead of the fused one (A/B measurements) */
+
 typedef struct nprsph_stats {
     uint64_t num_particles;
     uint64_t steps_done;
@@ -104,8 +107,8 @@ enum {
     NPRSPH_STAGE_CELLS,         /* cell-start table */
     NPRSPH_STAGE_REORDER,       /* gather pos/vel into cell order */
     NPRSPH_STAGE_RHO,           /* rho_pres_comp.glsl */
-    NPRSPH_STAGE_FORCE,         /* force_comp.glsl */
-    NPRSPH_STAGE_INTEGRATE,     /* integrate_comp.glsl (+ next-step keys) */
+    NPRSPH_STAGE_FORCE,         /* force_comp.glsl; in the fused step also integrate_comp.glsl */
+    NPRSPH_STAGE_INTEGRATE,     /* integrate_comp.glsl (+ next-step keys); ~0 when fused into FORCE */
     NPRSPH_NUM_STAGES
 };
 

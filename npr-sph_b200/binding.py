@@ -19,6 +19,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED, ERR_COMM = -1, -2, -3, -4, -5, -6
 FLAG_COUNT_NEIGHBOURS = 1
 FLAG_NO_HITMASK = 2
+FLAG_NO_FUSE = 4
 
 STAGES = ("keys", "sort", "cells", "reorder", "rho", "force", "integrate")
 DBG_SORTED_KEYS, DBG_SLOT_IDS, DBG_CELL_START, DBG_COUNTS_RHO, DBG_COUNTS_FORCE, DBG_LAST_PERM = range(6)

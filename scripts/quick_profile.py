@@ -27,7 +27,7 @@ if __name__ == "__main__":
     only = os.environ.get("QP_ONLY")            # "subdiv,flags" to run a single configuration
     for n1 in [int(a) for a in sys.argv[1:]] or [100, 256]:
         for subdiv in (1, 2):
-            for flags in (0, 2):
+            for flags in [int(f) for f in os.environ.get("QP_FLAGS", "0,2").split(",")]:
                 if only and only != f"{subdiv},{flags}":
                     continue
                 run(n1, subdiv, flags=flags)

@@ -158,6 +158,29 @@ def test_hitmask_and_rescan_force_paths_agree(sph, oracle):
     assert_field_close(out[0][0][:, 8:11], out[1][0][:, 8:11], "force (hit records vs rescan)", scale=scale)
 
 
+def test_fused_force_integrate_step_is_bit_identical_to_the_three_pass_step(sph, oracle):
+    """nprsph_step runs force + integrate as one launch when the column records exist; the
+    integrate arithmetic is the same op-by-op code on the same register values, so the fused
+    step must reproduce the three-launch step (FLAG_NO_FUSE) bit for bit, walls included."""
+    nx = 22
+    p = oracle.dam_break_params(nx, nx, nx)
+    p.upper[0] = (nx - 1) * 0.005 + 0.0015                                # a wall close enough to be hit
+    P = oracle.jitter(oracle.make_block(nx, nx, nx), 0.2 * 0.005, seed=11)
+    P[:, 4] = 1.0                                                          # everybody runs into the +x wall
+    out = []
+    for flags in (0, sph.FLAG_NO_FUSE):
+        sim = sph.Simulation(cell_subdiv=2, flags=flags)
+        sim.apply_params(p)
+        sim.upload(P)
+        sim.set_paused(False)
+        sim.step(25)
+        out.append(sim.download())
+        prof = sim.profile_step(2)
+        assert (prof["integrate"] < 0.5 * prof["force"]) if flags == 0 else prof["integrate"] > 0
+    assert (out[0][:, 0] >= np.float32(p.upper[0])).any(), "fixture should reach the +x wall"
+    assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
+
+
 def test_dense_clump_overflows_the_hitmask_gracefully(sph, oracle):
     """More candidates than the bitmask holds (reference default scene: ~1700 per particle with
     h = 4s at 160x rest density) must fall back to the re-test path with identical results."""
