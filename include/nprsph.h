@@ -182,6 +182,37 @@ int nprsph_debug_read(nprsph_ctx* ctx, int item, void* host_dst, uint64_t bytes)
 int nprsph_sort_pairs_host(int device, const uint32_t* keys_in, const uint32_t* vals_in,
                            uint64_t n, int key_bits, uint32_t* keys_out, uint32_t* vals_out);
 
+/* ---- live parameter surface (the "Constants Window" sliders, Main.cpp:240-247) ----------------- */
+enum {
+    NPRSPH_SLIDER_MASS = 0,         /* ImGui::SliderFloat("Mass", ..., 0.01, 0.1)              Main.cpp:242 */
+    NPRSPH_SLIDER_SMOOTHING,        /* "Smoothing" 7..10 (the default 4 lies outside)           Main.cpp:243 */
+    NPRSPH_SLIDER_VISCOSITY,        /* "Viscosity" 1000..5000                                   Main.cpp:244 */
+    NPRSPH_SLIDER_RESTING_DENSITY,  /* "Resting Density" 1000..5000                             Main.cpp:245 */
+    NPRSPH_NUM_SLIDERS
+};
+typedef struct nprsph_slider { const char* label; float min, max, def; } nprsph_slider;
+int nprsph_slider_info(int id, nprsph_slider* out);
+/* one slider edit: clamps to the widget's range, writes the ConstantsUniform field, takes effect at
+ * the next step (sendUniforms, Main.cpp:274-275) */
+int nprsph_set_slider(nprsph_ctx* ctx, int id, float value);
+
+/* ---- static colliders (new: README.md:59 "Add objects for particles to collide with") --------- */
+/* Applied by the integrate pass after the Euler update and before the box walls; the response is
+ * the reference's wall rule (integrate_comp.glsl:46-77): put the particle on the surface and
+ * multiply the normal velocity by -damping.  Not stored in snapshots. */
+#define NPRSPH_MAX_COLLIDERS 8
+enum { NPRSPH_COLLIDER_SPHERE = 0,  /* a = centre, b[0] = radius                */
+       NPRSPH_COLLIDER_BOX = 1 };   /* a = lower corner, b = upper corner       */
+typedef struct nprsph_collider {
+    uint32_t kind;
+    float a[3];
+    float b[3];
+    float reserved;
+} nprsph_collider;                  /* 32 bytes */
+int nprsph_set_colliders(nprsph_ctx* ctx, const nprsph_collider* list, int n);
+/* copies up to cap entries, returns the number of colliders set (negative: error) */
+int nprsph_get_colliders(const nprsph_ctx* ctx, nprsph_collider* out, int cap);
+
 /* ---- snapshots (new: the reference's state never leaves the GPU) ------------ */
 /* file = 256-byte header (parameters, n, step count), the slot table of the cell-ordered
  * arrangement and n 64-byte records in original order; a loaded run continues bit for bit */

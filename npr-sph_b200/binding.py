@@ -38,6 +38,20 @@ class Boundary(C.Structure):        # BoundaryUniform, Main.cpp:118-122
     _fields_ = [("upper", C.c_float * 4), ("lower", C.c_float * 4)]
 
 
+class Collider(C.Structure):        # nprsph_collider (static obstacles of the integrate pass)
+    _fields_ = [("kind", C.c_uint32), ("a", C.c_float * 3), ("b", C.c_float * 3),
+                ("reserved", C.c_float)]
+
+
+class Slider(C.Structure):          # nprsph_slider: one widget of the "Constants Window", Main.cpp:240-247
+    _fields_ = [("label", C.c_char_p), ("min", C.c_float), ("max", C.c_float), ("default", C.c_float)]
+
+
+COLLIDER_SPHERE, COLLIDER_BOX = 0, 1
+SLIDER_MASS, SLIDER_SMOOTHING, SLIDER_VISCOSITY, SLIDER_RESTING_DENSITY = range(4)
+MAX_COLLIDERS = 8
+
+
 class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("stream", C.c_void_p),
                 ("particle_radius", C.c_float), ("gas_const", C.c_float),
@@ -66,6 +80,10 @@ SYMBOLS = {
     "nprsph_set_constants": (C.c_int, [_P, C.POINTER(Constants)]),
     "nprsph_get_constants": (C.c_int, [_P, C.POINTER(Constants)]),
     "nprsph_set_boundary": (C.c_int, [_P, C.POINTER(Boundary)]),
+    "nprsph_slider_info": (C.c_int, [C.c_int, C.POINTER(Slider)]),
+    "nprsph_set_slider": (C.c_int, [_P, C.c_int, C.c_float]),
+    "nprsph_set_colliders": (C.c_int, [_P, C.POINTER(Collider), C.c_int]),
+    "nprsph_get_colliders": (C.c_int, [_P, C.POINTER(Collider), C.c_int]),
     "nprsph_get_boundary": (C.c_int, [_P, C.POINTER(Boundary)]),
     "nprsph_set_config": (C.c_int, [_P, C.POINTER(Config)]),
     "nprsph_get_config": (C.c_int, [_P, C.POINTER(Config)]),
@@ -201,6 +219,34 @@ class Simulation:
         b.upper[3] = upper[3] if len(upper) > 3 else 1.0
         b.lower[3] = lower[3] if len(lower) > 3 else 1.0
         self._ck(self.lib.nprsph_set_boundary(self._h, C.byref(b)))
+
+    def set_slider(self, slider_id: int, value: float):
+        """One edit of a "Constants Window" slider (Main.cpp:242-245): clamped to the widget's range."""
+        self._ck(self.lib.nprsph_set_slider(self._h, slider_id, value))
+
+    def slider_info(self, slider_id: int) -> Slider:
+        s = Slider()
+        self._ck(self.lib.nprsph_slider_info(slider_id, C.byref(s)))
+        return s
+
+    def set_colliders(self, colliders):
+        """colliders: sequence of ("sphere", centre, radius) / ("box", lower, upper) or Collider."""
+        arr = (Collider * max(1, len(colliders)))()
+        for i, c in enumerate(colliders):
+            if isinstance(c, Collider):
+                arr[i] = c
+            elif c[0] == "sphere":
+                arr[i] = Collider(COLLIDER_SPHERE, (C.c_float * 3)(*c[1]), (C.c_float * 3)(c[2], 0, 0), 0.0)
+            else:
+                arr[i] = Collider(COLLIDER_BOX, (C.c_float * 3)(*c[1]), (C.c_float * 3)(*c[2]), 0.0)
+        self._ck(self.lib.nprsph_set_colliders(self._h, arr, len(colliders)))
+
+    def get_colliders(self):
+        arr = (Collider * MAX_COLLIDERS)()
+        n = self.lib.nprsph_get_colliders(self._h, arr, MAX_COLLIDERS)
+        if n < 0:
+            self._ck(n)
+        return [arr[i] for i in range(n)]
 
     def get_boundary(self) -> Boundary:
         b = Boundary()

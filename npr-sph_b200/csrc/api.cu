@@ -234,7 +234,7 @@ int run_force(nprsph_ctx* c) {
 int run_integrate(nprsph_ctx* c) {
     // keys for the next step are written where the sort expects its input
     launch_integrate(c->pos[c->cur], c->vel[c->cur], c->frc[c->cur], c->keys[0], (uint32_t)c->n,
-                     c->grid, c->sph, c->stream);
+                     c->grid, c->sph, c->colliders, c->stream);
     c->keys_valid = true;
     c->grid_valid = false;
     c->mask_valid = false;
@@ -253,7 +253,7 @@ int run_force_integrate(nprsph_ctx* c, bool* fused_out, cudaEvent_t between /* n
     const bool fused = !(c->cfg.flags & NPRSPH_FLAG_NO_FUSE) &&
         launch_force_integrate(c->pos[c->cur], c->vel[c->cur], c->frc[nxt], c->cell_start, (uint32_t)c->n,
                                c->grid, c->sph, c->counts_force, c->mask_valid ? c->hitmask : nullptr,
-                               (uint32_t)c->cap, c->pos[nxt], c->vel[nxt], c->keys[0], c->stream);
+                               (uint32_t)c->cap, c->pos[nxt], c->vel[nxt], c->keys[0], c->colliders, c->stream);
     if (fused_out) *fused_out = fused;
     if (!fused) {
         run_force(c);
@@ -455,6 +455,68 @@ int nprsph_get_boundary(const nprsph_ctx* c, nprsph_boundary* b) {
     *b = c->bounds;
     return NPRSPH_OK;
 }
+// Static colliders: kernel parameters of the integrate kernels, so they take effect at the next
+// step like the uniform blocks (sendUniforms, Main.cpp:274-278).
+int nprsph_set_colliders(nprsph_ctx* c, const nprsph_collider* list, int n) {
+    if (!c || n < 0 || (n && !list)) return NPRSPH_ERR_INVALID;
+    if (n > NPRSPH_MAX_COLLIDERS) return fail(c, NPRSPH_ERR_INVALID, "more than NPRSPH_MAX_COLLIDERS colliders%s");
+    ColliderSet cs = {};
+    for (int i = 0; i < n; i++) {
+        const nprsph_collider& k = list[i];
+        if (k.kind == NPRSPH_COLLIDER_SPHERE) {
+            if (!(k.b[0] > 0.0f)) return fail(c, NPRSPH_ERR_INVALID, "sphere collider needs a positive radius%s");
+        } else if (k.kind == NPRSPH_COLLIDER_BOX) {
+            for (int a = 0; a < 3; a++)
+                if (!(k.a[a] < k.b[a])) return fail(c, NPRSPH_ERR_INVALID, "box collider needs lower < upper%s");
+        } else {
+            return fail(c, NPRSPH_ERR_INVALID, "unknown collider kind%s");
+        }
+        cs.a[i] = make_float4(k.a[0], k.a[1], k.a[2], (float)k.kind);
+        cs.b[i] = make_float4(k.b[0], k.b[1], k.b[2], 0.0f);
+    }
+    cs.n = n;
+    c->colliders = cs;
+    return NPRSPH_OK;
+}
+int nprsph_get_colliders(const nprsph_ctx* c, nprsph_collider* out, int cap) {
+    if (!c || cap < 0 || (cap && !out)) return NPRSPH_ERR_INVALID;
+    const int n = c->colliders.n < cap ? c->colliders.n : cap;
+    for (int i = 0; i < n; i++) {
+        const float4 a = c->colliders.a[i], b = c->colliders.b[i];
+        out[i].kind = (uint32_t)a.w;
+        out[i].a[0] = a.x; out[i].a[1] = a.y; out[i].a[2] = a.z;
+        out[i].b[0] = b.x; out[i].b[1] = b.y; out[i].b[2] = b.z;
+        out[i].reserved = 0.0f;
+    }
+    return c->colliders.n;
+}
+
+// The "Constants Window" of the reference GUI (Main.cpp:240-247): four ImGui::SliderFloat widgets
+// bound to ConstantsData.  A slider edit clamps to the widget's range; the stored defaults
+// (Main.cpp:110-116) may lie outside it (smoothing_coeff 4 vs a 7..10 slider) until touched.
+static const nprsph_slider g_sliders[NPRSPH_NUM_SLIDERS] = {
+    {"Mass", 0.01f, 0.1f, 0.02f},                   // Main.cpp:242
+    {"Smoothing", 7.0f, 10.0f, 4.0f},               // Main.cpp:243
+    {"Viscosity", 1000.0f, 5000.0f, 3000.0f},       // Main.cpp:244
+    {"Resting Density", 1000.0f, 5000.0f, 1000.0f}, // Main.cpp:245
+};
+int nprsph_slider_info(int id, nprsph_slider* out) {
+    if (id < 0 || id >= NPRSPH_NUM_SLIDERS || !out) return NPRSPH_ERR_INVALID;
+    *out = g_sliders[id];
+    return NPRSPH_OK;
+}
+int nprsph_set_slider(nprsph_ctx* c, int id, float value) {
+    if (!c) return NPRSPH_ERR_INVALID;
+    if (id < 0 || id >= NPRSPH_NUM_SLIDERS || value != value) return fail(c, NPRSPH_ERR_INVALID, "bad slider id or value%s");
+    const nprsph_slider& s = g_sliders[id];
+    const float v = value < s.min ? s.min : (value > s.max ? s.max : value);   // ImGui clamps the edit
+    float* field[NPRSPH_NUM_SLIDERS] = {&c->consts.mass, &c->consts.smoothing_coeff, &c->consts.visc,
+                                        &c->consts.resting_rho};
+    *field[id] = v;
+    c->params_dirty = true;
+    return NPRSPH_OK;
+}
+
 int nprsph_set_config(nprsph_ctx* c, const nprsph_config* cfg) {
     if (!c) return NPRSPH_ERR_INVALID;
     if (!config_ok(cfg)) return fail(c, NPRSPH_ERR_INVALID, "bad nprsph_config%s");

@@ -101,4 +101,80 @@ __device__ __forceinline__ float eos_pressure(float rho, const SphDev& s) {
 }
 
 
+// ---- pass 3 for one particle ----------------------------------------------------------------------------
+// Static colliders (README.md:59 "Add objects for particles to collide with"):
+// not in the reference's shaders; the response mirrors its wall rule (integrate_comp.glsl:46-77:
+// put the particle on the surface, multiply the normal velocity by -DAMPING).  Kernel parameter of
+// the integrate kernels only.  a.w = kind (0 sphere: a.xyz centre, b.x radius; 1 box: a.xyz lower
+// corner, b.xyz upper corner).  Restated op for op in oracle/sph_oracle.c:collide_one.
+constexpr int MAX_COLLIDERS = 8;
+struct ColliderSet {
+    int n;
+    int pad[3];
+    float4 a[MAX_COLLIDERS];
+    float4 b[MAX_COLLIDERS];
+};
+
+__device__ __forceinline__ void collide_sphere(float4& p, float4& v, float cx, float cy, float cz,
+                                               float R, float damping) {
+    const float dx = __fsub_rn(p.x, cx), dy = __fsub_rn(p.y, cy), dz = __fsub_rn(p.z, cz);
+    const float r2 = dist2_exact(dx, dy, dz);
+    if (!(r2 < __fmul_rn(R, R))) return;
+    const float r = __fsqrt_rn(r2);
+    float nx = 0.0f, ny = 1.0f, nz = 0.0f;                   // a particle exactly at the centre leaves upwards
+    if (r > 0.0f) { nx = __fdiv_rn(dx, r); ny = __fdiv_rn(dy, r); nz = __fdiv_rn(dz, r); }
+    p.x = __fadd_rn(cx, __fmul_rn(R, nx));
+    p.y = __fadd_rn(cy, __fmul_rn(R, ny));
+    p.z = __fadd_rn(cz, __fmul_rn(R, nz));
+    const float vn = __fadd_rn(__fadd_rn(__fmul_rn(v.x, nx), __fmul_rn(v.y, ny)), __fmul_rn(v.z, nz));
+    const float k = __fmul_rn(__fadd_rn(1.0f, damping), vn);    // v_n -> -damping * v_n
+    v.x = __fsub_rn(v.x, __fmul_rn(k, nx));
+    v.y = __fsub_rn(v.y, __fmul_rn(k, ny));
+    v.z = __fsub_rn(v.z, __fmul_rn(k, nz));
+}
+
+__device__ __forceinline__ void collide_box(float4& p, float4& v, const float4& lo, const float4& hi,
+                                            float damping) {
+    if (!(p.x > lo.x && p.x < hi.x && p.y > lo.y && p.y < hi.y && p.z > lo.z && p.z < hi.z)) return;
+    // nearest face, first minimum in the order -x, +x, -y, +y, -z, +z
+    const float pen[6] = {__fsub_rn(p.x, lo.x), __fsub_rn(hi.x, p.x), __fsub_rn(p.y, lo.y),
+                          __fsub_rn(hi.y, p.y), __fsub_rn(p.z, lo.z), __fsub_rn(hi.z, p.z)};
+    int best = 0;
+    float bp = pen[0];
+#pragma unroll
+    for (int f = 1; f < 6; f++) if (pen[f] < bp) { bp = pen[f]; best = f; }
+    const float nd = -damping;
+    if (best == 0)      { p.x = lo.x; v.x = __fmul_rn(v.x, nd); }
+    else if (best == 1) { p.x = hi.x; v.x = __fmul_rn(v.x, nd); }
+    else if (best == 2) { p.y = lo.y; v.y = __fmul_rn(v.y, nd); }
+    else if (best == 3) { p.y = hi.y; v.y = __fmul_rn(v.y, nd); }
+    else if (best == 4) { p.z = lo.z; v.z = __fmul_rn(v.z, nd); }
+    else                { p.z = hi.z; v.z = __fmul_rn(v.z, nd); }
+}
+
+// integrate_comp.glsl:35-82 for one particle: a = F/rho, v += dt a, x += dt v (:41-43), then the
+// colliders (extension), then the box walls (:46-77).  The shader's arithmetic operation by
+// operation (no contraction), so given identical inputs the result is bit-identical to the oracle's.
+__device__ __forceinline__ void integrate_particle(float4& p, float4& v, const float4& f,
+                                                   const SphDev& sp, const ColliderSet& cs) {
+    const float rho = v.w, nd = -sp.damping;
+    v.x = __fadd_rn(v.x, __fmul_rn(sp.dt, __fdiv_rn(f.x, rho)));
+    v.y = __fadd_rn(v.y, __fmul_rn(sp.dt, __fdiv_rn(f.y, rho)));
+    v.z = __fadd_rn(v.z, __fmul_rn(sp.dt, __fdiv_rn(f.z, rho)));
+    p.x = __fadd_rn(p.x, __fmul_rn(sp.dt, v.x));
+    p.y = __fadd_rn(p.y, __fmul_rn(sp.dt, v.y));
+    p.z = __fadd_rn(p.z, __fmul_rn(sp.dt, v.z));
+    for (int c = 0; c < cs.n; c++) {
+        const float4 a = cs.a[c], b = cs.b[c];
+        if (a.w == 0.0f) collide_sphere(p, v, a.x, a.y, a.z, b.x, sp.damping);
+        else             collide_box(p, v, a, b, sp.damping);
+    }
+    if (p.x < sp.lower[0])      { p.x = sp.lower[0]; v.x = __fmul_rn(v.x, nd); }
+    else if (p.x > sp.upper[0]) { p.x = sp.upper[0]; v.x = __fmul_rn(v.x, nd); }
+    if (p.y < sp.lower[1])      { p.y = sp.lower[1]; v.y = __fmul_rn(v.y, nd); }
+    else if (p.y > sp.upper[1]) { p.y = sp.upper[1]; v.y = __fmul_rn(v.y, nd); }
+    if (p.z < sp.lower[2])      { p.z = sp.lower[2]; v.z = __fmul_rn(v.z, nd); }
+    else if (p.z > sp.upper[2]) { p.z = sp.upper[2]; v.z = __fmul_rn(v.z, nd); }
+}
+
 }  // namespace nprsph

@@ -32,6 +32,7 @@ struct nprsph_ctx {
     float4* vel[2] = {nullptr, nullptr};
     float4* frc[2] = {nullptr, nullptr};
     int cur = 0;
+    nprsph::ColliderSet colliders = {};         // static obstacles of the integrate pass (nprsph_set_colliders)
     uint32_t* keys[2] = {nullptr, nullptr};
     uint32_t* vals[2] = {nullptr, nullptr};
     uint32_t* sorted_keys = nullptr;

@@ -230,27 +230,16 @@ k_cells_slab(const uint32_t* __restrict__ skeys, uint32_t baseA, uint32_t lenA, 
 }
 
 // integrate_comp.glsl:35-82 on the own slots + next-step slab keys (same arithmetic as k_integrate)
-__device__ __forceinline__ void integrate_axis(float& x, float& v, float f, float rho, float lo,
-                                               float up, const SphDev& sp) {
-    const float a = __fdiv_rn(f, rho);
-    v = __fadd_rn(v, __fmul_rn(sp.dt, a));
-    x = __fadd_rn(x, __fmul_rn(sp.dt, v));
-    if (x < lo)      { x = lo; v = __fmul_rn(v, -sp.damping); }
-    else if (x > up) { x = up; v = __fmul_rn(v, -sp.damping); }
-}
-
 __global__ void __launch_bounds__(TPB)
 k_integrate_slab(float4* __restrict__ posid, float4* __restrict__ velrho,
                  const float4* __restrict__ forcep, uint32_t* __restrict__ keys, uint32_t n,
-                 GridDev g, SphDev sp, int W, int R) {
+                 GridDev g, SphDev sp, int W, int R, const __grid_constant__ ColliderSet cs) {
     const uint32_t i = blockIdx.x * TPB + threadIdx.x;
     if (i >= n) return;
     float4 p = posid[i];
     float4 v = velrho[i];
     const float4 f = forcep[i];
-    integrate_axis(p.x, v.x, f.x, v.w, sp.lower[0], sp.upper[0], sp);
-    integrate_axis(p.y, v.y, f.y, v.w, sp.lower[1], sp.upper[1], sp);
-    integrate_axis(p.z, v.z, f.z, v.w, sp.lower[2], sp.upper[2], sp);
+    integrate_particle(p, v, f, sp, cs);
     posid[i] = p;
     velrho[i] = v;
     keys[i] = cell_key_slab(p.x, p.y, p.z, g, W, R);
@@ -589,7 +578,7 @@ int step_group(nprsph_ctx** cs, int n, cudaEvent_t* ev = nullptr) {
         if (d->n_own)
             k_integrate_slab<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
                 c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off,
-                c->keys[0], d->n_own, d->lg, c->sph, d->W, d->R);
+                c->keys[0], d->n_own, d->lg, c->sph, d->W, d->R, c->colliders);
         CK(c, cudaGetLastError());
         d->prepared = false;                        // positions moved: keys/ghosts/table are stale
         d->steps_done++;

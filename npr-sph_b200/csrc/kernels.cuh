@@ -41,8 +41,10 @@ void launch_force(const float4* posid, const float4* velrho, float4* forcep,
 bool launch_force_integrate(const float4* posid, const float4* velrho, float4* forcep,
                             const uint32_t* cell_start, uint32_t n, const GridDev& g, const SphDev& sp,
                             uint32_t* counts_by_id, const uint32_t* records_or_null, uint32_t rec_stride,
-                            float4* pos_next, float4* vel_next, uint32_t* keys_next, cudaStream_t st);
+                            float4* pos_next, float4* vel_next, uint32_t* keys_next,
+                            const ColliderSet& cs, cudaStream_t st);
 void launch_integrate(float4* posid, float4* velrho, const float4* forcep, uint32_t* keys,
-                      uint32_t n, const GridDev& g, const SphDev& sp, cudaStream_t st);
+                      uint32_t n, const GridDev& g, const SphDev& sp, const ColliderSet& cs,
+                      cudaStream_t st);
 
 }  // namespace nprsph

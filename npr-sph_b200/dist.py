@@ -97,6 +97,10 @@ class SlabGroup:
         for s in self.sims:
             s.apply_params(p)
 
+    def set_colliders(self, colliders):
+        for s in self.sims:
+            s.set_colliders(colliders)
+
     def set_paused(self, paused: bool):
         for s in self.sims:
             s.set_paused(paused)

@@ -28,6 +28,20 @@ class Params(C.Structure):
     ]
 
 
+class Collider(C.Structure):
+    """kind 0: sphere (a = centre, b[0] = radius); kind 1: box (a = lower, b = upper corner)."""
+    _fields_ = [("kind", C.c_uint32), ("a", C.c_float * 3), ("b", C.c_float * 3),
+                ("reserved", C.c_float)]
+
+
+def sphere(centre, radius) -> "Collider":
+    return Collider(0, (C.c_float * 3)(*centre), (C.c_float * 3)(radius, 0.0, 0.0), 0.0)
+
+
+def box(lower, upper) -> "Collider":
+    return Collider(1, (C.c_float * 3)(*lower), (C.c_float * 3)(*upper), 0.0)
+
+
 class Grid(C.Structure):
     _fields_ = [
         ("lo", C.c_float * 3), ("inv_cell", C.c_float), ("dim", C.c_int32 * 3),
@@ -68,6 +82,7 @@ def lib():
         L.oracle_pass_rho.argtypes = [fp, C.c_int, pp, u32p]
         L.oracle_pass_force.argtypes = [fp, C.c_int, pp, u32p]
         L.oracle_pass_integrate.argtypes = [fp, C.c_int, pp]
+        L.oracle_pass_integrate_colliders.argtypes = [fp, C.c_int, pp, C.POINTER(Collider), C.c_int]
         L.oracle_step.argtypes = [fp, C.c_int, pp, C.c_int]
         L.oracle_force_scale.argtypes = [fp, C.c_int, pp, fp]
         L.oracle_sample_update.argtypes = [fp, C.c_int, pp, i32p, C.c_int, fp]
@@ -165,8 +180,12 @@ def force_scale(P, p) -> np.ndarray:
     return out
 
 
-def pass_integrate(P, p):
-    lib().oracle_pass_integrate(_fp(P), len(P), C.byref(p))
+def pass_integrate(P, p, colliders=None):
+    if colliders:
+        arr = (Collider * len(colliders))(*colliders)
+        lib().oracle_pass_integrate_colliders(_fp(P), len(P), C.byref(p), arr, len(colliders))
+    else:
+        lib().oracle_pass_integrate(_fp(P), len(P), C.byref(p))
 
 
 def step(P, p, n_steps=1, grid=0):

@@ -227,11 +227,52 @@ void oracle_force_scale(const float* P, int n, const oracle_params* p, float* sc
 }
 
 /* ---- integrate_comp.glsl:35-82 ---------------------------------------------------- */
-static void integrate_one(float* r, const oracle_params* p) {
+/* Static colliders: NOT in the reference (README.md:59 lists them as future work).  This is the
+ * specification the CUDA path (common.cuh:collide_sphere / collide_box) is held to bit for bit:
+ * the reference's wall rule (integrate_comp.glsl:46-77) applied to the obstacle's surface. */
+static void collide_one(float* r, const oracle_collider* c, float damping) {
+    float* x = r; float* v = r + 4;
+    if (c->kind == 0) {                                   /* sphere: a = centre, b[0] = radius */
+        const float R = c->b[0];
+        const float dx = x[0] - c->a[0], dy = x[1] - c->a[1], dz = x[2] - c->a[2];
+        const float xx = dx * dx, yy = dy * dy, zz = dz * dz;
+        const float r2 = (xx + yy) + zz;
+        const float RR = R * R;
+        if (!(r2 < RR)) return;
+        const float rr = sqrtf(r2);
+        float n[3] = {0.0f, 1.0f, 0.0f};
+        if (rr > 0.0f) { n[0] = dx / rr; n[1] = dy / rr; n[2] = dz / rr; }
+        for (int k = 0; k < 3; k++) { const float t = R * n[k]; x[k] = c->a[k] + t; }
+        const float t0 = v[0] * n[0], t1 = v[1] * n[1], t2 = v[2] * n[2];
+        const float vn = (t0 + t1) + t2;
+        const float e = 1.0f + damping;
+        const float kk = e * vn;
+        for (int k = 0; k < 3; k++) { const float t = kk * n[k]; v[k] = v[k] - t; }
+    } else {                                              /* box: a = lower, b = upper corner */
+        for (int k = 0; k < 3; k++) if (!(x[k] > c->a[k] && x[k] < c->b[k])) return;
+        int best = 0; float bp = x[0] - c->a[0];
+        for (int f = 1; f < 6; f++) {
+            const int k = f >> 1;
+            const float pen = (f & 1) ? c->b[k] - x[k] : x[k] - c->a[k];
+            if (pen < bp) { bp = pen; best = f; }
+        }
+        const int k = best >> 1;
+        x[k] = (best & 1) ? c->b[k] : c->a[k];
+        v[k] = v[k] * -damping;
+    }
+}
+
+static void integrate_one(float* r, const oracle_params* p, const oracle_collider* cs, int nc) {
     for (int k = 0; k < 3; k++) {
         float a = r[8 + k] / r[12];                                         /* :41 */
         float v = r[4 + k] + p->dt * a;                                     /* :42 */
         float x = r[k] + p->dt * v;                                         /* :43 */
+        r[4 + k] = v;
+        r[k] = x;
+    }
+    for (int c = 0; c < nc; c++) collide_one(r, cs + c, p->damping);
+    for (int k = 0; k < 3; k++) {
+        float v = r[4 + k], x = r[k];
         if (x < p->lower[k])      { x = p->lower[k]; v *= -p->damping; }    /* :46-77 */
         else if (x > p->upper[k]) { x = p->upper[k]; v *= -p->damping; }
         r[4 + k] = v;                                                       /* :80 */
@@ -241,7 +282,13 @@ static void integrate_one(float* r, const oracle_params* p) {
 
 void oracle_pass_integrate(float* P, int n, const oracle_params* p) {
 #pragma omp parallel for schedule(static)
-    for (int i = 0; i < n; i++) integrate_one(P + (size_t)i * ORACLE_REC, p);
+    for (int i = 0; i < n; i++) integrate_one(P + (size_t)i * ORACLE_REC, p, NULL, 0);
+}
+
+void oracle_pass_integrate_colliders(float* P, int n, const oracle_params* p,
+                                     const oracle_collider* cs, int nc) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) integrate_one(P + (size_t)i * ORACLE_REC, p, cs, nc);
 }
 
 /* display() compute block, Main.cpp:293-304: rho -> barrier -> force -> barrier -> integrate */
@@ -282,7 +329,7 @@ void oracle_sample_update(const float* P, int n, const oracle_params* p, const i
             force_term(rec, P + (size_t)j * ORACLE_REC, h, p->mass, spiky, lap, &a);
         }
         force_finish(rec, &a, p, rec + 8);
-        integrate_one(rec, p);
+        integrate_one(rec, p, NULL, 0);
     }
 }
 

@@ -40,6 +40,15 @@ typedef struct oracle_params {
     float pi;                /* rho_pres_comp.glsl:8  */
 } oracle_params;
 
+/* Static collider (extension, same layout as nprsph_collider): kind 0 sphere (a = centre,
+ * b[0] = radius), kind 1 box (a = lower corner, b = upper corner). */
+typedef struct oracle_collider {
+    uint32_t kind;
+    float a[3];
+    float b[3];
+    float reserved;
+} oracle_collider;
+
 /* Uniform-grid definition shared (as a specification) with the CUDA path.
  * Not part of the reference; restated here so keys can be compared bit-exactly. */
 typedef struct oracle_grid {
@@ -64,6 +73,8 @@ float oracle_r2_threshold(float h);
 void oracle_pass_rho(float* particles, int n, const oracle_params* p, uint32_t* counts);
 void oracle_pass_force(float* particles, int n, const oracle_params* p, uint32_t* counts);
 void oracle_pass_integrate(float* particles, int n, const oracle_params* p);
+void oracle_pass_integrate_colliders(float* particles, int n, const oracle_params* p,
+                                     const oracle_collider* cs, int nc);
 /* sum of |terms| of the force sums per particle/component (conditioning scale for tests) */
 void oracle_force_scale(const float* particles, int n, const oracle_params* p, float* scale3);
 void oracle_step(float* particles, int n, const oracle_params* p, int n_steps);

@@ -84,6 +84,83 @@ def test_parameter_edits_take_effect_at_the_next_step(sph, oracle):
     assert np.abs(G[:, :3] - P[:, :3]).max() < 1e-6
 
 
+def test_constants_window_sliders(sph, oracle):
+    """the four ImGui sliders of the reference's "Constants Window"
+    (Main.cpp:242-245).  An edit clamps to the widget's range and is seen by the next step."""
+    sim = sph.Simulation()
+    want = {sph.SLIDER_MASS: (b"Mass", 0.01, 0.1, 0.02), sph.SLIDER_SMOOTHING: (b"Smoothing", 7.0, 10.0, 4.0),
+            sph.SLIDER_VISCOSITY: (b"Viscosity", 1000.0, 5000.0, 3000.0),
+            sph.SLIDER_RESTING_DENSITY: (b"Resting Density", 1000.0, 5000.0, 1000.0)}
+    for sid, (label, lo, hi, default) in want.items():
+        s = sim.slider_info(sid)
+        assert (s.label, s.min, s.max, s.default) == (label, np.float32(lo), np.float32(hi), np.float32(default))
+    c = sim.get_constants()
+    assert (c.mass, c.smoothing_coeff) == (np.float32(0.02), 4.0)      # defaults may lie outside the range
+    sim.set_slider(sph.SLIDER_SMOOTHING, 3.0)                           # dragging clamps: 7..10
+    sim.set_slider(sph.SLIDER_MASS, 0.05)
+    sim.set_slider(sph.SLIDER_VISCOSITY, 9e9)
+    c = sim.get_constants()
+    assert (c.smoothing_coeff, c.mass, c.visc, c.resting_rho) == (7.0, np.float32(0.05), 5000.0, 1000.0)
+    with pytest.raises(sph.NprSphError):
+        sim.set_slider(17, 1.0)
+    # the edit reaches the next dispatch: density of the default block with h = 7 * radius
+    p = oracle.default_params()
+    p.smoothing_coeff, p.mass, p.visc = 7.0, 0.05, 5000.0
+    P = oracle.make_block(6, 8, 6)
+    sim.upload(P)
+    sim.pass_rho()
+    oracle.pass_rho(P, p)
+    G = sim.download()
+    assert np.abs(G[:, 12] - P[:, 12]).max() / P[:, 12].max() < 1e-5
+
+
+def test_static_colliders_match_the_oracle_spec_bit_for_bit(sph, oracle):
+    """SURVEY.md 8(f)-4 / README.md:59: sphere and box obstacles in the integrate pass.  Same
+    inputs -> the integrate pass with colliders is bit-identical to the oracle's restatement; the
+    fused and the three-launch step agree bit for bit; no particle ends a step inside an obstacle."""
+    nx = 20
+    p = oracle.dam_break_params(nx, nx, nx)
+    s = 0.005
+    cols = [("sphere", (0.12, 0.3 * nx * s, 0.6 * nx * s), 0.02),
+            ("box", (0.1, -s, 0.0), (0.11, 0.5 * nx * s, 0.25 * nx * s))]
+    ocols = [oracle.sphere(cols[0][1], cols[0][2]), oracle.box(cols[1][1], cols[1][2])]
+    P = oracle.jitter(oracle.make_block(nx, nx, nx), 0.2 * s, seed=21)
+    P[:, 4] = 1.5                                            # the block flies into the obstacles
+    outs = []
+    for flags in (0, sph.FLAG_NO_FUSE):
+        sim = sph.Simulation(cell_subdiv=2, flags=flags)
+        sim.apply_params(p)
+        sim.set_colliders(cols)
+        got = sim.get_colliders()
+        assert len(got) == 2 and got[0].kind == sph.COLLIDER_SPHERE and got[1].kind == sph.COLLIDER_BOX
+        sim.upload(P)
+        sim.set_paused(False)
+        hit = False
+        for _ in range(12):
+            sim.step(10)
+            G = sim.download()
+            d = np.linalg.norm(G[:, :3].astype(np.float64) - np.array(cols[0][1]), axis=1)
+            assert d.min() >= cols[0][2] * (1 - 1e-6), "a particle ended a step inside the sphere"
+            lo, hi = np.float32(cols[1][1]), np.float32(cols[1][2])
+            inside = ((G[:, :3] > lo) & (G[:, :3] < hi)).all(axis=1)
+            assert not inside.any(), "a particle ended a step inside the box"
+            hit = hit or (d < 1.02 * cols[0][2]).any()
+        assert hit, "fixture should reach the sphere"
+        outs.append(G)
+        if flags:       # pass level: identical inputs -> identical bits
+            sim.pass_rho(); sim.pass_force()
+            A = sim.download()
+            sim.pass_integrate()
+            B = sim.download()
+            oracle.pass_integrate(A, p, ocols)
+            assert np.array_equal(A[:, :8].view(np.uint32), B[:, :8].view(np.uint32))
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    with pytest.raises(sph.NprSphError):
+        sim.set_colliders([("sphere", (0, 0, 0), -1.0)])
+    with pytest.raises(sph.NprSphError):
+        sim.set_colliders([("sphere", (0, 0, 0), 1.0)] * 9)
+
+
 def test_upload_download_roundtrip_and_device_pointer(sph):
     rng = np.random.default_rng(0)
     rec = rng.normal(size=(1234, 16)).astype(np.float32)

@@ -62,6 +62,10 @@ def test_migration_and_ghosts_under_strong_flow(sph, oracle):
     grp.apply_params(p)
     grp.scene_block(nx, ny, nz, 0.005, None, 3e-4, 11)
     grp.set_paused(False)
+    # an obstacle in the stream: every slab applies the same colliders
+    cols = [("sphere", (0.25, 0.02, 0.025), 0.02)]
+    ref.set_colliders(cols)
+    grp.set_colliders(cols)
     n = nx * ny * nz
     for chunk in range(8):
         ref.step(15)

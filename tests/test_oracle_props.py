@@ -81,3 +81,32 @@ def test_cell_keys_cover_every_neighbour(oracle):
         i, j = np.nonzero(r < np.float32(h))
         for c in (cx, cy, cz):
             assert np.abs(c[i] - c[j]).max() <= k
+
+
+def test_collider_spec_of_the_oracle(oracle):
+    """Static colliders are an extension (README.md:59 future work); the oracle is their
+    specification.  A particle that ends a step inside an obstacle is put on its surface and its
+    normal velocity is multiplied by -damping, like the box walls (integrate_comp.glsl:46-77)."""
+    p = oracle.dam_break_params(4, 4, 4)
+    p.dt = 1e-3
+    P = np.zeros((4, 16), np.float32)
+    P[:, 3] = 1.0
+    P[:, 12] = 1000.0                                       # rho (force stays 0: pure advection)
+    P[0, :3] = (0.010, 0.010, 0.0055); P[0, 4:7] = (0.0, 0.0, 1.0)     # flies into the sphere from -z
+    P[1, :3] = (0.010, 0.010, 0.010); P[1, 4:7] = (0.0, 0.0, 0.0)     # sits at the sphere's centre
+    P[2, :3] = (0.0301, 0.010, 0.010); P[2, 4:7] = (-1.0, 0.5, 0.0)   # enters the box through its +x face
+    P[3, :3] = (0.015, 0.018, 0.010); P[3, 4:7] = (0.1, 0.1, 0.1)     # touches nothing
+    cs = [oracle.sphere((0.010, 0.010, 0.010), 0.004), oracle.box((0.020, 0.0, 0.0), (0.030, 0.02, 0.02))]
+    Q = P.copy()
+    oracle.pass_integrate(P, p, cs)
+    oracle.pass_integrate(Q, p)                              # no colliders
+    c, R = np.float32([0.010, 0.010, 0.010]), np.float32(0.004)
+    # 0: on the sphere's surface below the centre, vz reflected and damped
+    assert np.linalg.norm(P[0, :3] - c) == pytest.approx(R, rel=1e-6) and P[0, 2] < c[2]
+    assert P[0, 6] == pytest.approx(-p.damping * 1.0, rel=1e-6) and P[0, 4] == 0 and P[0, 5] == 0
+    # 1: pushed out along +y
+    assert tuple(P[1, :3]) == (c[0], np.float32(c[1] + R), c[2])
+    # 2: back on the +x face, vx reflected, vy untouched
+    assert P[2, 0] == np.float32(0.030) and P[2, 4] == np.float32(p.damping) and P[2, 5] == np.float32(0.5)
+    # 3: identical to the collider-free pass
+    assert np.array_equal(P[3], Q[3])
