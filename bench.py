@@ -242,8 +242,7 @@ class SlabRunner:
         self.cap = int(info.cap_own)
         st = self.grp.sims[0].stats()
         self.grid_cells = (info.x_end - info.x_begin + 2 * st.cell_subdiv) * st.grid_dim[1] * st.grid_dim[2]
-        bits = max(1, int(self.grid_cells + 2).bit_length())
-        self.sort_passes = min(-(-bits // 8), -(-bits // 9))     # 9-bit digits when they save a pass
+        self.sort_passes = int(info.sort_passes)                 # over the occupied x layers only
         # classify + hist + P onesweep + gather + 2 ghost keys + cells + fill + rho + force + integrate
         self.launches_per_step = 10 + self.sort_passes
         self.fused = False

@@ -250,6 +250,7 @@ typedef struct nprsph_dist_info {
     int32_t  x_begin, x_end;    /* owned global x cell range */
     uint64_t num_own, ghosts_left, ghosts_right, nan_particles;
     uint64_t migrated_total, steps_done, cap_own, cap_ghost;
+    uint32_t sort_bits, sort_passes;   /* key bits / digit passes of the last step's slab sort */
 } nprsph_dist_info;
 
 /* count-balanced slab boundaries from a per-x-plane particle histogram (pure host code):

@@ -18,6 +18,9 @@
 //   k_force, k_integrate (+ next keys; a particle that left the slab gets GONE_L / GONE_R)
 #include "dist.cuh"
 
+#include <stdlib.h>
+#include <time.h>
+
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
@@ -82,11 +85,19 @@ constexpr int TPB = 256;
 inline unsigned blocks_for(uint64_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 
 // ---- kernels ---------------------------------------------------------------------------------------
+// Sentinel keys of the slab sort.  All high bits set, so a sort on the low b bits keeps them behind
+// every cell key (in this order) as long as the cell keys stay below 2^b - 4: the digit passes
+// only have to cover the OCCUPIED part of the local grid (prepare_group), not the long empty
+// stretch of box the last rank of a dam break owns.
+constexpr uint32_t KEY_NAN = 0xFFFFFFFCu;       // stays on its rank for ever, in no cell
+constexpr uint32_t KEY_GONE_L = 0xFFFFFFFDu;    // belongs to the left rank
+constexpr uint32_t KEY_GONE_R = 0xFFFFFFFEu;    // belongs to the right rank
+
 __device__ __forceinline__ uint32_t cell_key_slab(float x, float y, float z, const GridDev& g, int W, int R) {
-    if (pos_is_nan(x, y, z)) return g.num_cells;                 // stays on its rank for ever
+    if (pos_is_nan(x, y, z)) return KEY_NAN;
     const int cxl = cell_x_unclamped(x, g);
-    if (cxl < R) return g.num_cells + 1u;                        // GONE_L: belongs to the left rank
-    if (cxl >= R + W) return g.num_cells + 2u;                   // GONE_R
+    if (cxl < R) return KEY_GONE_L;
+    if (cxl >= R + W) return KEY_GONE_R;
     const int cy = cell_coord(y, g.lo[1], g.inv_cell, g.dim[1]);
     const int cz = cell_coord(z, g.lo[2], g.inv_cell, g.dim[2]);
     return ((uint32_t)cxl * (uint32_t)g.dim[1] + (uint32_t)cy) * (uint32_t)g.dim[2] + (uint32_t)cz;
@@ -133,11 +144,11 @@ k_classify(const uint32_t* __restrict__ keys, const float4* __restrict__ posid,
            Migrant* __restrict__ sendL, Migrant* __restrict__ sendR, uint32_t cap_mig,
            uint32_t* __restrict__ counts) {
     const uint32_t s = blockIdx.x * TPB + threadIdx.x;
-    const uint32_t key = (s < n) ? keys[s] : 0xFFFFFFFFu;
+    const uint32_t key = (s < n) ? keys[s] : 0xFFFFFFFFu;      // (out of range: none of the classes below)
     const uint32_t plane = (uint32_t)g.dim[1] * (uint32_t)g.dim[2];
-    const bool goneL = key == g.num_cells + 1u, goneR = key == g.num_cells + 2u;
-    const bool isnan = key == g.num_cells;
-    const bool valid = key < g.num_cells;
+    const bool goneL = key == KEY_GONE_L, goneR = key == KEY_GONE_R;
+    const bool isnan = key == KEY_NAN;
+    const bool valid = key < KEY_NAN;
     const uint32_t cxl = valid ? key / plane : 0u;
     const bool inL = valid && cxl < (uint32_t)(2 * R);
     const bool inR = valid && cxl >= (uint32_t)W;
@@ -182,7 +193,7 @@ k_unpack_migrants(const Migrant* __restrict__ recv, const uint32_t* __restrict__
     const uint32_t key = cell_key_slab(m.posid.x, m.posid.y, m.posid.z, g, W, R);
     keys[t] = key;
     // an immigrant must land in the boundary layer next to the rank it came from
-    if (key >= g.num_cells) counts[CNT_ERR_IMMIGRANT] = 1u;
+    if (key >= KEY_NAN) counts[CNT_ERR_IMMIGRANT] = 1u;
 }
 
 __global__ void __launch_bounds__(TPB)
@@ -336,7 +347,7 @@ int setup_local_grid(nprsph_ctx* c) {
     if (cells + 4 >= (1ull << 32)) return fail(c, NPRSPH_ERR_INVALID, "local grid too large%s");
     d->lg.num_cells = (uint32_t)cells;
     int bits = 1;
-    while (bits < 32 && (1ull << bits) <= cells + 2) bits++;     // keys 0..num_cells+2
+    while (bits < 32 && (1ull << bits) < cells + 4) bits++;      // cell keys below 2^bits - 4 (sentinels)
     d->key_bits = bits;
     const size_t need = (size_t)cells + 4;
     if (need > c->cell_cap) {
@@ -386,10 +397,33 @@ int alloc_slab(nprsph_ctx* c, uint64_t cap_own, uint64_t cap_ghost, uint64_t cap
     return NPRSPH_OK;
 }
 
+// NPRSPH_DIST_TRACE=1: synchronise after every phase of prepare_group and report the mean wall time
+// of each on stderr every 20 steps (a diagnostic: the synchronisation serialises the step).
+struct PhaseTrace {
+    bool on = getenv("NPRSPH_DIST_TRACE") != nullptr;
+    double acc[8] = {0}, t0 = 0;
+    int steps = 0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    void begin(nprsph_ctx** cs, int n) { if (!on) return; for (int r = 0; r < n; r++) cudaStreamSynchronize(cs[r]->stream); t0 = now(); }
+    void mark(nprsph_ctx** cs, int n, int phase) {
+        if (!on) return;
+        for (int r = 0; r < n; r++) cudaStreamSynchronize(cs[r]->stream);
+        const double t = now(); acc[phase] += t - t0; t0 = t;
+    }
+    void end(int rank) {
+        if (!on || ++steps % 20) return;
+        fprintf(stderr, "[nprsph dist trace] rank %d, mean ms over %d steps: classify+counts+sync %.3f | migrants %.3f | "
+                "unpack+sort %.3f | gather %.3f | ghost positions %.3f | ghost keys+cell table %.3f\n", rank, steps,
+                acc[0] / steps, acc[1] / steps, acc[2] / steps, acc[3] / steps, acc[4] / steps, acc[5] / steps);
+    }
+};
+static PhaseTrace g_trace;
+
 // Everything between "positions + unsorted slab keys of the own particles are final" and "cell
 // table and ghosts are ready for k_rho", for all local ranks in lock step.
 int prepare_group(nprsph_ctx** cs, int n) {
     Xfer x[64];
+    g_trace.begin(cs, n);
     // (1) classify + counter exchange, one host sync
     for (int r = 0; r < n; r++) {
         nprsph_ctx* c = cs[r]; DistState* d = c->dist;
@@ -411,6 +445,7 @@ int prepare_group(nprsph_ctx** cs, int n) {
                               cudaMemcpyDeviceToHost, c->stream));
     }
     for (int r = 0; r < n; r++) CK(cs[r], cudaStreamSynchronize(cs[r]->stream));
+    g_trace.mark(cs, n, 0);
 
     // (2) sizes, migrant exchange
     uint32_t inL[64], inR[64], leaveL[64], leaveR[64], dropped[64];
@@ -451,6 +486,7 @@ int prepare_group(nprsph_ctx** cs, int n) {
     }
     rc = exchange_group(cs, n, x);
     if (rc) return rc;
+    g_trace.mark(cs, n, 1);
 
     // (3) immigrants behind the own particles (ascending id), sort, gather into [own_off, ...)
     for (int r = 0; r < n; r++) {
@@ -476,8 +512,14 @@ int prepare_group(nprsph_ctx** cs, int n) {
         }
         const uint32_t n_new = n_pre - (d->first_prepare ? dropped[r] : leaveL[r] + leaveR[r]);
         bool in_b = false;
-        CK(c, sort_pairs(c->keys[0], c->vals[0], c->keys[1], c->vals[1], n_pre, d->key_bits, true,
+        // digit passes over the occupied x layers only (KEY_* sentinels sort behind them)
+        int bits = 1;
+        const uint64_t span = (uint64_t)(d->x_top + 1u) * (uint32_t)d->lg.dim[1] * (uint32_t)d->lg.dim[2] + 4u;
+        while (bits < d->key_bits && (1ull << bits) < span) bits++;
+        d->sort_bits = bits;
+        CK(c, sort_pairs(c->keys[0], c->vals[0], c->keys[1], c->vals[1], n_pre, bits, true,
                          c->sort_ws, c->num_sms, c->stream, &in_b));
+        if (g_trace.on && r == n - 1) g_trace.mark(cs, n, 2);
         const int nxt = 1 - c->cur;
         if (n_new)
             k_gather_slab<<<blocks_for(n_new), TPB, 0, c->stream>>>(
@@ -494,8 +536,10 @@ int prepare_group(nprsph_ctx** cs, int n) {
                 p + d->own_off - d->gL, d->gL * sizeof(float4),
                 p + d->own_off + d->n_own, d->gR * sizeof(float4)};
     }
+    g_trace.mark(cs, n, 3);
     rc = exchange_group(cs, n, x);
     if (rc) return rc;
+    g_trace.mark(cs, n, 4);
 
     // (5) ghost keys + cell table over [ghost L | own | ghost R]
     for (int r = 0; r < n; r++) {
@@ -512,6 +556,8 @@ int prepare_group(nprsph_ctx** cs, int n) {
         launch_fill_gaps(c->gap_list, c->gap_count, c->cell_start, c->num_sms, c->stream);
         CK(c, cudaGetLastError());
     }
+    g_trace.mark(cs, n, 5);
+    g_trace.end(cs[0]->dist->rank);
     return NPRSPH_OK;
 }
 
@@ -874,6 +920,8 @@ int nprsph_dist_get_info(nprsph_ctx* c, nprsph_dist_info* out) {
     out->migrated_total = d->migrated_total; out->steps_done = d->steps_done;
     out->cap_own = d->cap_own; out->cap_ghost = d->cap_ghost;
     out->nan_particles = d->n_nan;
+    out->sort_bits = (uint32_t)d->sort_bits;
+    out->sort_passes = (uint32_t)sort_num_passes(d->sort_bits);
     return NPRSPH_OK;
 }
 

@@ -22,7 +22,8 @@ struct DistState {
     // slab geometry (global x cell indices) and the local grid derived from ctx->grid
     int X0 = 0, X1 = 0, W = 0, R = 1;
     GridDev lg;
-    int key_bits = 1;
+    int key_bits = 1;                  // bits of the largest cell key of the local grid (+ sentinels)
+    int sort_bits = 1;                 // bits the last prepare actually sorted on (occupied x layers)
     bool ready = false;                // scene distributed
     bool prepared = false;             // ownership, ghosts and cell table match the current positions
 

@@ -29,7 +29,8 @@ class DistInfo(C.Structure):
                 ("x_end", C.c_int32), ("num_own", C.c_uint64), ("ghosts_left", C.c_uint64),
                 ("ghosts_right", C.c_uint64), ("nan_particles", C.c_uint64),
                 ("migrated_total", C.c_uint64), ("steps_done", C.c_uint64),
-                ("cap_own", C.c_uint64), ("cap_ghost", C.c_uint64)]
+                ("cap_own", C.c_uint64), ("cap_ghost", C.c_uint64),
+                ("sort_bits", C.c_uint32), ("sort_passes", C.c_uint32)]
 
 
 def unique_id() -> bytes:
