@@ -136,15 +136,13 @@ k_slab_scene(float4* __restrict__ posid, float4* __restrict__ velrho, uint32_t* 
     keys[t] = cell_key_slab(c[0], c[1], c[2], g, W, R);
 }
 
-// own keys (unsorted, as written by k_integrate_slab) -> leavers into the migration buffers,
-// boundary-layer / NaN counts.  send == nullptr: leavers are only counted (scene distribution).
-__global__ void __launch_bounds__(TPB)
-k_classify(const uint32_t* __restrict__ keys, const float4* __restrict__ posid,
-           const float4* __restrict__ velrho, uint32_t n, GridDev g, int W, int R,
-           Migrant* __restrict__ sendL, Migrant* __restrict__ sendR, uint32_t cap_mig,
-           uint32_t* __restrict__ counts) {
-    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
-    const uint32_t key = (s < n) ? keys[s] : 0xFFFFFFFFu;      // (out of range: none of the classes below)
+// One own particle's new key -> leaver into the migration buffer, boundary-layer / NaN counts.
+// Every lane of the warp calls it (key 0xFFFFFFFF for lanes without a particle).
+// send == nullptr: leavers are only counted (scene distribution).
+__device__ __forceinline__ void classify_key(uint32_t key, const float4& p, const float4& v, const GridDev& g,
+                                             int W, int R, Migrant* __restrict__ sendL,
+                                             Migrant* __restrict__ sendR, uint32_t cap_mig,
+                                             uint32_t* __restrict__ counts) {
     const uint32_t plane = (uint32_t)g.dim[1] * (uint32_t)g.dim[2];
     const bool goneL = key == KEY_GONE_L, goneR = key == KEY_GONE_R;
     const bool isnan = key == KEY_NAN;
@@ -156,7 +154,7 @@ k_classify(const uint32_t* __restrict__ keys, const float4* __restrict__ posid,
         const uint32_t slot = atomicAdd(counts + (goneL ? CNT_LEAVE_L : CNT_LEAVE_R), 1u);
         Migrant* dst = goneL ? sendL : sendR;
         if (dst) {
-            if (slot < cap_mig) { dst[slot].posid = posid[s]; dst[slot].velrho = velrho[s]; }
+            if (slot < cap_mig) { dst[slot].posid = p; dst[slot].velrho = v; }
             else counts[CNT_ERR_OVERFLOW] = 1u;
         }
     }
@@ -168,10 +166,33 @@ k_classify(const uint32_t* __restrict__ keys, const float4* __restrict__ posid,
         if (mR) atomicAdd(counts + CNT_HALO_R, (uint32_t)__popc(mR));
         if (mN) atomicAdd(counts + CNT_NAN, (uint32_t)__popc(mN));
     }
-    // highest occupied x layer: the cell table only has to reach `reach` layers beyond it (the
-    // last rank of a dam break owns a long empty stretch of the box)
+    // highest occupied x layer: the cell table and the sort only have to reach `reach` layers
+    // beyond it (the last rank of a dam break owns a long empty stretch of the box).  Reduced per
+    // block and checked against the current value first: half a million warps hammering one L2
+    // address -- with an atomic or with a load -- cost more than the rest of the kernel.
+    __shared__ uint32_t s_xmax;
+    if (threadIdx.x == 0) s_xmax = 0u;
+    __syncthreads();
     const uint32_t xm = __reduce_max_sync(0xffffffffu, cxl);
-    if (lane == 0 && xm) atomicMax(counts + CNT_XMAX, xm);
+    if (lane == 0 && xm) atomicMax(&s_xmax, xm);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_xmax > __ldcg(counts + CNT_XMAX)) atomicMax(counts + CNT_XMAX, s_xmax);
+}
+
+// stand-alone classification of unsorted own keys (after a scene / upload; a step classifies
+// inside k_integrate_slab)
+__global__ void __launch_bounds__(TPB)
+k_classify(const uint32_t* __restrict__ keys, const float4* __restrict__ posid,
+           const float4* __restrict__ velrho, uint32_t n, GridDev g, int W, int R,
+           Migrant* __restrict__ sendL, Migrant* __restrict__ sendR, uint32_t cap_mig,
+           uint32_t* __restrict__ counts) {
+    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    const bool live = s < n;
+    const uint32_t key = live ? keys[s] : 0xFFFFFFFFu;         // (out of range: none of the classes)
+    const bool gone = key == KEY_GONE_L || key == KEY_GONE_R;
+    const float4 p = (gone && sendL) ? posid[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = (gone && sendL) ? velrho[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+    classify_key(key, p, v, g, W, R, sendL, sendR, cap_mig, counts);
 }
 
 __global__ void __launch_bounds__(TPB)
@@ -196,64 +217,86 @@ k_unpack_migrants(const Migrant* __restrict__ recv, const uint32_t* __restrict__
     if (key >= KEY_NAN) counts[CNT_ERR_IMMIGRANT] = 1u;
 }
 
-__global__ void __launch_bounds__(TPB)
-k_gather_slab(const uint32_t* __restrict__ sorted_keys, const uint32_t* __restrict__ perm,
-              const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
-              float4* __restrict__ pos_out, float4* __restrict__ vel_out,
-              uint32_t* __restrict__ skeys, uint32_t n) {
-    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t src = perm[s];
-    pos_out[s] = pos_in[src];
-    vel_out[s] = vel_in[src];
-    skeys[s] = sorted_keys[s];
-}
-
-__global__ void __launch_bounds__(TPB)
-k_ghost_keys(const float4* __restrict__ posid, uint32_t* __restrict__ skeys, uint32_t n, GridDev g) {
-    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
-    if (t >= n) return;
-    const float4 p = posid[t];
-    skeys[t] = cell_key(p.x, p.y, p.z, g);
-}
-
-// Lower-bound cell table over the logical concatenation  A = slots [baseA, baseA+lenA)  (ghost L +
-// valid own), B = slots [baseB, baseB+lenB) (ghost R); own particles with NaN positions sit
-// between A and B and are in no cell.  table has table_len entries.
-__global__ void __launch_bounds__(TPB)
-k_cells_slab(const uint32_t* __restrict__ skeys, uint32_t baseA, uint32_t lenA, uint32_t baseB,
-             uint32_t lenB, uint32_t* __restrict__ table, uint32_t table_len,
-             uint4* __restrict__ gap_list, uint32_t* __restrict__ gap_count) {
-    const uint32_t l = blockIdx.x * TPB + threadIdx.x;
-    const uint32_t total = lenA + lenB;
-    if (l > total) return;
-    auto slot_of = [&](uint32_t q) { return q < lenA ? baseA + q : baseB + (q - lenA); };
-    const uint32_t slot = (l < total) ? slot_of(l) : baseB + lenB;
-    const uint32_t key_here = (l < total) ? skeys[slot] : table_len - 1u;
-    const uint32_t lo = (l == 0) ? 0u : skeys[slot_of(l - 1)] + 1u;
-    if (key_here < lo) return;
-    const uint32_t len = key_here - lo + 1u;
+// ---- cell table of a slab ---------------------------------------------------------------------------
+// Lower-bound table over the slots [ghost L | own (valid) | own (NaN) | ghost R].  Ghost-L keys lie
+// in x layers [0, R), own keys in [R, R+W), ghost-R keys in [R+W, W+2R): three independent regions
+// of the table.  The own region is written by the gather kernel (before any ghost has arrived),
+// the two ghost regions by k_ghost_cells once the neighbours' boundary-layer positions are in.
+// An element q of a sorted run [0, len] (q == len: the tail) fills the cells (key[q-1], key[q]]
+// with its slot; long empty runs are queued for k_fill_gaps (grid.cu).
+__device__ __forceinline__ void fill_cells(uint32_t lo, uint32_t hi, uint32_t slot,
+                                           uint32_t* __restrict__ table, uint4* __restrict__ gap_list,
+                                           uint32_t* __restrict__ gap_count) {
+    if (hi < lo || hi == 0xFFFFFFFFu) return;
+    const uint32_t len = hi - lo + 1u;
     if (len <= GAP_INLINE) {
-        for (uint32_t c = lo; c <= key_here; c++) table[c] = slot;
-    } else {                                   // long empty run: filled cooperatively (grid.cu)
+        for (uint32_t c = lo; c <= hi; c++) table[c] = slot;
+    } else {
         gap_list[atomicAdd(gap_count, 1u)] = make_uint4(lo, len, slot, 0u);
     }
 }
 
-// integrate_comp.glsl:35-82 on the own slots + next-step slab keys (same arithmetic as k_integrate)
+// Gather of the own particles into sorted order + the own region of the cell table.
+// n: own particles after migration; n_valid of them (the first) have cells, the rest are NaN.
+// Cells [cell_lo, cell_hi] belong to the region; cells above the last own key hold tail_slot (the
+// first ghost-R slot: the NaN block in between is harmless, a NaN candidate is never a hit).
+__global__ void __launch_bounds__(TPB)
+k_gather_cells_slab(const uint32_t* __restrict__ sorted_keys, const uint32_t* __restrict__ perm,
+                    const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
+                    float4* __restrict__ pos_out, float4* __restrict__ vel_out, uint32_t n,
+                    uint32_t n_valid, uint32_t slot_base, uint32_t tail_slot, uint32_t cell_lo,
+                    uint32_t cell_hi, uint32_t* __restrict__ table, uint4* __restrict__ gap_list,
+                    uint32_t* __restrict__ gap_count) {
+    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    if (s < n) {
+        const uint32_t src = perm[s];
+        pos_out[s] = pos_in[src];
+        vel_out[s] = vel_in[src];
+    }
+    if (s > n_valid) return;
+    const uint32_t lo = (s == 0) ? cell_lo : max(sorted_keys[s - 1] + 1u, cell_lo);
+    const uint32_t hi = (s < n_valid) ? min(sorted_keys[s], cell_hi) : cell_hi;
+    fill_cells(lo, hi, (s < n_valid) ? slot_base + s : tail_slot, table, gap_list, gap_count);
+}
+
+// One ghost block: keys from the received positions (the same arithmetic every rank uses for a
+// cell) + its region [cell_lo, cell_hi] of the table; cells above the last ghost key hold tail_slot.
+__global__ void __launch_bounds__(TPB)
+k_ghost_cells(const float4* __restrict__ posid, uint32_t n, uint32_t slot_base, uint32_t tail_slot,
+              uint32_t cell_lo, uint32_t cell_hi, GridDev g, uint32_t* __restrict__ table,
+              uint4* __restrict__ gap_list, uint32_t* __restrict__ gap_count) {
+    const uint32_t q = blockIdx.x * TPB + threadIdx.x;
+    if (q > n) return;
+    uint32_t prev = 0u, here = 0u;
+    if (q > 0) { const float4 p = posid[q - 1]; prev = cell_key(p.x, p.y, p.z, g); }
+    if (q < n) { const float4 p = posid[q]; here = cell_key(p.x, p.y, p.z, g); }
+    const uint32_t lo = (q == 0) ? cell_lo : max(prev + 1u, cell_lo);
+    const uint32_t hi = (q < n) ? min(here, cell_hi) : cell_hi;
+    fill_cells(lo, hi, (q < n) ? slot_base + q : tail_slot, table, gap_list, gap_count);
+}
+
 __global__ void __launch_bounds__(TPB)
 k_integrate_slab(float4* __restrict__ posid, float4* __restrict__ velrho,
                  const float4* __restrict__ forcep, uint32_t* __restrict__ keys, uint32_t n,
-                 GridDev g, SphDev sp, int W, int R, const __grid_constant__ ColliderSet cs) {
+                 GridDev g, SphDev sp, int W, int R, const __grid_constant__ ColliderSet cs,
+                 Migrant* __restrict__ sendL, Migrant* __restrict__ sendR, uint32_t cap_mig,
+                 uint32_t* __restrict__ counts) {
     const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-    if (i >= n) return;
-    float4 p = posid[i];
-    float4 v = velrho[i];
-    const float4 f = forcep[i];
-    integrate_particle(p, v, f, sp, cs);
-    posid[i] = p;
-    velrho[i] = v;
-    keys[i] = cell_key_slab(p.x, p.y, p.z, g, W, R);
+    uint32_t key = 0xFFFFFFFFu;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p;
+    if (i < n) {
+        p = posid[i];
+        v = velrho[i];
+        const float4 f = forcep[i];
+        integrate_particle(p, v, f, sp, cs);
+        posid[i] = p;
+        velrho[i] = v;
+        key = cell_key_slab(p.x, p.y, p.z, g, W, R);
+        keys[i] = key;
+    }
+    // the next step's classification (leavers, boundary layers, NaN, top layer) while the particle
+    // is in registers
+    classify_key(key, p, v, g, W, R, sendL, sendR, cap_mig, counts);
 }
 
 __global__ void __launch_bounds__(TPB)
@@ -384,7 +427,6 @@ int alloc_slab(nprsph_ctx* c, uint64_t cap_own, uint64_t cap_ghost, uint64_t cap
         CK(c, realloc_dev(c->counts_rho, total));
         CK(c, realloc_dev(c->counts_force, total));
     }
-    CK(c, realloc_dev(d->skeys, total));
     CK(c, realloc_dev(d->sendL, cap_mig));
     CK(c, realloc_dev(d->sendR, cap_mig));
     CK(c, realloc_dev(d->recv, 2 * cap_mig));
@@ -413,7 +455,7 @@ struct PhaseTrace {
     void end(int rank) {
         if (!on || ++steps % 20) return;
         fprintf(stderr, "[nprsph dist trace] rank %d, mean ms over %d steps: classify+counts+sync %.3f | migrants %.3f | "
-                "unpack+sort %.3f | gather %.3f | ghost positions %.3f | ghost keys+cell table %.3f\n", rank, steps,
+                "unpack+sort %.3f | gather+own cells %.3f | ghost positions %.3f | ghost cells+gaps %.3f\n", rank, steps,
                 acc[0] / steps, acc[1] / steps, acc[2] / steps, acc[3] / steps, acc[4] / steps, acc[5] / steps);
     }
 };
@@ -428,12 +470,15 @@ int prepare_group(nprsph_ctx** cs, int n) {
     for (int r = 0; r < n; r++) {
         nprsph_ctx* c = cs[r]; DistState* d = c->dist;
         CK(c, cudaSetDevice(c->cfg.device));
-        CK(c, cudaMemsetAsync(d->d_counts, 0, 3 * CNT_WORDS * sizeof(uint32_t), c->stream));
-        if (d->n_own)
-            k_classify<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
+        if (!d->classified) {
+            CK(c, cudaMemsetAsync(d->d_counts, 0, 3 * CNT_WORDS * sizeof(uint32_t), c->stream));
+            if (d->n_own)
+                k_classify<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
                 c->keys[0], c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, d->n_own, d->lg,
                 d->W, d->R, d->first_prepare ? nullptr : d->sendL, d->first_prepare ? nullptr : d->sendR,
                 d->cap_mig, d->d_counts);
+        }
+        d->classified = false;
         x[r] = {d->d_counts, CNT_WORDS * 4, d->d_counts, CNT_WORDS * 4,
                 d->d_counts + CNT_WORDS, CNT_WORDS * 4, d->d_counts + 2 * CNT_WORDS, CNT_WORDS * 4};
     }
@@ -521,10 +566,16 @@ int prepare_group(nprsph_ctx** cs, int n) {
                          c->sort_ws, c->num_sms, c->stream, &in_b));
         if (g_trace.on && r == n - 1) g_trace.mark(cs, n, 2);
         const int nxt = 1 - c->cur;
-        if (n_new)
-            k_gather_slab<<<blocks_for(n_new), TPB, 0, c->stream>>>(
+        {   // gather + own region of the cell table (layers [R, R+W), up to the last layer in use)
+            const uint32_t plane = (uint32_t)d->lg.dim[1] * (uint32_t)d->lg.dim[2];
+            const uint32_t table_len = (d->x_top + 1u) * plane + 4u;
+            const uint32_t own_hi = ((d->rank + 1 < d->world) ? (uint32_t)(d->R + d->W) * plane : table_len) - 1u;
+            CK(c, cudaMemsetAsync(c->gap_count, 0, sizeof(uint32_t), c->stream));
+            k_gather_cells_slab<<<blocks_for((uint64_t)n_new + 1), TPB, 0, c->stream>>>(
                 in_b ? c->keys[1] : c->keys[0], in_b ? c->vals[1] : c->vals[0], pos, vel,
-                c->pos[nxt] + d->own_off, c->vel[nxt] + d->own_off, d->skeys + d->own_off, n_new);
+                c->pos[nxt] + d->own_off, c->vel[nxt] + d->own_off, n_new, n_new - d->n_nan, d->own_off,
+                d->own_off + n_new, (uint32_t)d->R * plane, own_hi, c->cell_start, c->gap_list, c->gap_count);
+        }
         c->cur = nxt;
         d->n_own = n_new;
         d->first_prepare = false;
@@ -541,18 +592,21 @@ int prepare_group(nprsph_ctx** cs, int n) {
     if (rc) return rc;
     g_trace.mark(cs, n, 4);
 
-    // (5) ghost keys + cell table over [ghost L | own | ghost R]
+    // (5) ghost regions of the cell table (layers [0, R) and [R+W, W+2R)), then the long empty runs
     for (int r = 0; r < n; r++) {
         nprsph_ctx* c = cs[r]; DistState* d = c->dist;
         CK(c, cudaSetDevice(c->cfg.device));
-        float4* p = c->pos[c->cur];
-        if (d->gL) k_ghost_keys<<<blocks_for(d->gL), TPB, 0, c->stream>>>(p + d->own_off - d->gL, d->skeys + d->own_off - d->gL, d->gL, d->lg);
-        if (d->gR) k_ghost_keys<<<blocks_for(d->gR), TPB, 0, c->stream>>>(p + d->own_off + d->n_own, d->skeys + d->own_off + d->n_own, d->gR, d->lg);
-        const uint32_t lenA = d->gL + d->n_own - d->n_nan, lenB = d->gR;
-        CK(c, cudaMemsetAsync(c->gap_count, 0, sizeof(uint32_t), c->stream));
-        k_cells_slab<<<blocks_for((uint64_t)lenA + lenB + 1), TPB, 0, c->stream>>>(
-            d->skeys, d->own_off - d->gL, lenA, d->own_off + d->n_own, lenB, c->cell_start,
-            (d->x_top + 1u) * (uint32_t)d->lg.dim[1] * (uint32_t)d->lg.dim[2] + 4u, c->gap_list, c->gap_count);
+        const float4* p = c->pos[c->cur];
+        const uint32_t plane = (uint32_t)d->lg.dim[1] * (uint32_t)d->lg.dim[2];
+        const uint32_t table_len = (d->x_top + 1u) * plane + 4u;
+        // left: always written (without a left neighbour the layers [0, R) are empty and hold own_off)
+        k_ghost_cells<<<blocks_for((uint64_t)d->gL + 1), TPB, 0, c->stream>>>(
+            p + d->own_off - d->gL, d->gL, d->own_off - d->gL, d->own_off, 0u, (uint32_t)d->R * plane - 1u,
+            d->lg, c->cell_start, c->gap_list, c->gap_count);
+        if (d->rank + 1 < d->world)
+            k_ghost_cells<<<blocks_for((uint64_t)d->gR + 1), TPB, 0, c->stream>>>(
+                p + d->own_off + d->n_own, d->gR, d->own_off + d->n_own, d->own_off + d->n_own + d->gR,
+                (uint32_t)(d->R + d->W) * plane, table_len - 1u, d->lg, c->cell_start, c->gap_list, c->gap_count);
         launch_fill_gaps(c->gap_list, c->gap_count, c->cell_start, c->num_sms, c->stream);
         CK(c, cudaGetLastError());
     }
@@ -621,10 +675,13 @@ int step_group(nprsph_ctx** cs, int n, cudaEvent_t* ev = nullptr) {
         launch_force(P, V, c->frc[0], c->cell_start, in1, own_end - in1, d->lg, c->sph, nullptr,
                      c->hitmask, d->cap_total, c->stream);
         if (ev && r == 0) CK(c, cudaEventRecord(ev[4], c->stream));
+        CK(c, cudaMemsetAsync(d->d_counts, 0, 3 * CNT_WORDS * sizeof(uint32_t), c->stream));
         if (d->n_own)
             k_integrate_slab<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
                 c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off,
-                c->keys[0], d->n_own, d->lg, c->sph, d->W, d->R, c->colliders);
+                c->keys[0], d->n_own, d->lg, c->sph, d->W, d->R, c->colliders, d->sendL, d->sendR,
+                d->cap_mig, d->d_counts);
+        d->classified = true;                       // counts and migration buffers are ready
         CK(c, cudaGetLastError());
         d->prepared = false;                        // positions moved: keys/ghosts/table are stale
         d->steps_done++;
@@ -655,7 +712,7 @@ void nprsph::dist_destroy(nprsph_ctx* c) {
     DistState* d = c->dist;
     if (!d) return;
     if (d->nccl_comm && nccl() && nccl()->CommDestroy) nccl()->CommDestroy((ncclComm_t)d->nccl_comm);
-    cudaFree(d->sendL); cudaFree(d->sendR); cudaFree(d->recv); cudaFree(d->skeys);
+    cudaFree(d->sendL); cudaFree(d->sendR); cudaFree(d->recv);
     cudaFree(d->d_counts); cudaFree(d->mig_ids); cudaFree(d->mig_sort_ws);
     if (d->h_counts) cudaFreeHost(d->h_counts);
     if (d->comm_stream) { cudaStreamSynchronize(d->comm_stream); cudaStreamDestroy(d->comm_stream); }
@@ -793,6 +850,7 @@ int nprsph_dist_scene_block(nprsph_ctx* c, int nx, int ny, int nz, float spacing
     d->n_own = (uint32_t)n_cand;
     d->first_prepare = true;
     d->prepared = false;
+    d->classified = false;
     d->ready = true;
     d->steps_done = 0;
     d->migrated_total = 0;
@@ -878,6 +936,7 @@ int nprsph_dist_upload(nprsph_ctx* c, const nprsph_particle* records, const uint
     d->n_own = (uint32_t)n;
     d->first_prepare = true;         // records that belong to another slab are dropped, not sent
     d->prepared = false;
+    d->classified = false;
     return NPRSPH_OK;
 }
 

@@ -26,6 +26,8 @@ struct DistState {
     int sort_bits = 1;                 // bits the last prepare actually sorted on (occupied x layers)
     bool ready = false;                // scene distributed
     bool prepared = false;             // ownership, ghosts and cell table match the current positions
+    bool classified = false;           // d_counts / sendL / sendR already hold the classification of keys[0]
+                                       // (k_integrate_slab did it); cleared by anything else that rewrites keys
 
     // slot layout: [ghost L | own | ghost R]; own particles start at slot own_off
     uint32_t cap_ghost = 0, cap_own = 0, cap_mig = 0, cap_total = 0, own_off = 0;
@@ -35,7 +37,6 @@ struct DistState {
     uint64_t migrated_total = 0, steps_done = 0;
 
     Migrant *sendL = nullptr, *sendR = nullptr, *recv = nullptr;
-    uint32_t* skeys = nullptr;         // sorted key of every slot
     uint32_t* d_counts = nullptr;      // [3][CNT_WORDS]: mine, from left, from right
     uint32_t* h_counts = nullptr;      // pinned mirror
     uint32_t* mig_ids = nullptr;       // [4][2*cap_mig] scratch: ids, iota, sorted ids, order

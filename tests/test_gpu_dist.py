@@ -81,6 +81,48 @@ def test_migration_and_ghosts_under_strong_flow(sph, oracle):
     grp.close()
 
 
+def test_nan_particles_stay_put_and_touch_nobody(sph, oracle):
+    """A particle with a NaN position has no cell: it stays on its rank behind the valid own
+    particles (between them and the right ghosts in slot order) and is nobody's neighbour, in
+    slab mode exactly as in the single context (the reference scene NaNs too)."""
+    from nprsph_b200.dist import SlabGroup
+    nx, ny, nz = 30, 12, 10
+    p = _scene(oracle, nx, ny, nz)
+    n = nx * ny * nz
+    ref = sph.Simulation(cell_subdiv=2)
+    ref.apply_params(p)
+    ref.scene_block(nx, ny, nz, 0.005, None, 2e-4, 3)
+    ref.set_paused(False)
+    grp = SlabGroup.local(3, cell_subdiv=2)
+    grp.apply_params(p)
+    grp.scene_block(nx, ny, nz, 0.005, None, 2e-4, 3)
+    grp.set_paused(False)
+    ref.step(5)
+    grp.step(5)
+    bad = np.array([7, n // 2 + 3, n - 5, n // 3])             # spread over the slabs
+    A = ref.download()
+    A[bad, 0] = np.nan
+    ref.upload(A)
+    hit = 0
+    for w in range(3):
+        rec, ids = grp.download(w)
+        m = np.isin(ids, bad)
+        hit += int(m.sum())
+        rec[m, 0] = np.nan
+        rec = np.ascontiguousarray(rec)
+        grp.upload_ptr(w, rec.ctypes.data, ids.ctypes.data, len(ids))
+    assert hit == len(bad)
+    for chunk in range(3):
+        ref.step(10)
+        grp.step(10)
+        A, G = ref.download(), grp.gather(n)
+        assert np.isnan(G[bad, 0]).all() and np.isnan(G[:, 0]).sum() == len(bad)
+        for name, cols in (("pos", POS), ("vel", VEL), ("rho", RHO)):
+            assert_field_close(G[:, cols], A[:, cols], f"{name}@{10 * (chunk + 1)}", elementwise=False)
+    assert sum(grp.info(w).nan_particles for w in range(3)) == len(bad)
+    grp.close()
+
+
 def test_world_of_one_is_the_plain_step(sph, oracle):
     from nprsph_b200.dist import SlabGroup
     p = _scene(oracle, 10, 10, 10)
