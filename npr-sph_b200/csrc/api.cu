@@ -405,8 +405,10 @@ int nprsph_create(const nprsph_config* cfg, nprsph_ctx** out) {
         if (e != cudaSuccess) { delete c; return fail(nullptr, NPRSPH_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         c->own_stream = true;
     }
-    e = cudaMalloc(&c->gap_count, 32);    // [0] gap count, [2..3] NaN counter, [4..5] tail state of the cell table
-    if (e == cudaSuccess) e = cudaMemset(c->gap_count, 0xFF, 32);
+    // [0] medium-gap count, [1] huge-gap count, [2..3] NaN counter, [4..5] tail state of the cell table,
+    // [8..] huge-gap list (common.cuh:push_gap)
+    e = cudaMalloc(&c->gap_count, GAP_CTL_BYTES);
+    if (e == cudaSuccess) e = cudaMemset(c->gap_count, 0xFF, GAP_CTL_BYTES);
     if (e != cudaSuccess) { nprsph_destroy(c); return fail(nullptr, NPRSPH_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
     int rc = build_scene(c);      // initOpenGL() -> init_particles(), Main.cpp:567
     if (rc) { g_create_error = c->err; nprsph_destroy(c); return rc; }

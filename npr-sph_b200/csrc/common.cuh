@@ -101,6 +101,24 @@ __device__ __forceinline__ float eos_pressure(float rho, const SphDev& s) {
 }
 
 
+// ---- empty runs of the cell table -------------------------------------------------------------------------
+// A thread of the table builders fills short empty runs itself and queues the others for
+// k_fill_gaps (grid.cu): medium runs in gap_list (one thread block each), the few huge ones (the
+// empty stretch of box ahead of a dam break) in a small list every block works on together.
+// ctl words: [0] medium-run count, [1] huge-run count; huge entries start at word 8.
+constexpr uint32_t GAP_INLINE = 64;          // runs up to this length are written by the finder
+constexpr uint32_t GAP_HUGE = 1u << 17;      // runs from this length on are filled by the whole grid
+constexpr uint32_t GAP_HUGE_MAX = 64;        // capacity of the huge-run list (overflow: medium list)
+constexpr size_t GAP_CTL_BYTES = 32 + GAP_HUGE_MAX * sizeof(uint4);
+__device__ __forceinline__ void push_gap(uint32_t lo, uint32_t len, uint32_t slot,
+                                         uint4* __restrict__ gap_list, uint32_t* __restrict__ ctl) {
+    if (len >= GAP_HUGE) {
+        const uint32_t k = atomicAdd(ctl + 1, 1u);
+        if (k < GAP_HUGE_MAX) { reinterpret_cast<uint4*>(ctl + 8)[k] = make_uint4(lo, len, slot, 0u); return; }
+    }
+    gap_list[atomicAdd(ctl, 1u)] = make_uint4(lo, len, slot, 0u);
+}
+
 // ---- pass 3 for one particle ----------------------------------------------------------------------------
 // Static colliders (README.md:59 "Add objects for particles to collide with"):
 // not in the reference's shaders; the response mirrors its wall rule (integrate_comp.glsl:46-77:

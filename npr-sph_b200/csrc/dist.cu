@@ -232,7 +232,7 @@ __device__ __forceinline__ void fill_cells(uint32_t lo, uint32_t hi, uint32_t sl
     if (len <= GAP_INLINE) {
         for (uint32_t c = lo; c <= hi; c++) table[c] = slot;
     } else {
-        gap_list[atomicAdd(gap_count, 1u)] = make_uint4(lo, len, slot, 0u);
+        push_gap(lo, len, slot, gap_list, gap_count);
     }
 }
 
@@ -570,7 +570,7 @@ int prepare_group(nprsph_ctx** cs, int n) {
             const uint32_t plane = (uint32_t)d->lg.dim[1] * (uint32_t)d->lg.dim[2];
             const uint32_t table_len = (d->x_top + 1u) * plane + 4u;
             const uint32_t own_hi = ((d->rank + 1 < d->world) ? (uint32_t)(d->R + d->W) * plane : table_len) - 1u;
-            CK(c, cudaMemsetAsync(c->gap_count, 0, sizeof(uint32_t), c->stream));
+            CK(c, cudaMemsetAsync(c->gap_count, 0, 2 * sizeof(uint32_t), c->stream));
             k_gather_cells_slab<<<blocks_for((uint64_t)n_new + 1), TPB, 0, c->stream>>>(
                 in_b ? c->keys[1] : c->keys[0], in_b ? c->vals[1] : c->vals[0], pos, vel,
                 c->pos[nxt] + d->own_off, c->vel[nxt] + d->own_off, n_new, n_new - d->n_nan, d->own_off,

@@ -99,19 +99,27 @@ k_reorder_cells(const uint32_t* __restrict__ sorted_keys, const uint32_t* __rest
     if (len <= GAP_INLINE) {
         for (uint32_t c = lo; c <= key_here; c++) cell_start[c] = s;
     } else {
-        const uint32_t slot = atomicAdd(gap_count, 1u);
-        gap_list[slot] = make_uint4(lo, len, s, 0u);
+        push_gap(lo, len, s, gap_list, gap_count);
     }
 }
 
+// Medium runs: one thread block each, round robin (an evolved dam break has ~10^5 of them; with
+// every block looping over the whole list this kernel took longer than the gather).  Huge runs:
+// all blocks together.
 __global__ void __launch_bounds__(TPB)
 k_fill_gaps(const uint4* __restrict__ gap_list, const uint32_t* __restrict__ gap_count,
             uint32_t* __restrict__ cell_start) {
-    const uint32_t gaps = *gap_count;
+    const uint32_t huge = min(gap_count[1], GAP_HUGE_MAX);
+    const uint4* huge_list = reinterpret_cast<const uint4*>(gap_count + 8);
     const uint32_t stride = gridDim.x * TPB;
-    for (uint32_t gi = 0; gi < gaps; gi++) {
-        const uint4 g = gap_list[gi];
+    for (uint32_t gi = 0; gi < huge; gi++) {
+        const uint4 g = huge_list[gi];
         for (uint32_t o = blockIdx.x * TPB + threadIdx.x; o < g.y; o += stride) cell_start[g.x + o] = g.z;
+    }
+    const uint32_t gaps = gap_count[0];
+    for (uint32_t gi = blockIdx.x; gi < gaps; gi += gridDim.x) {
+        const uint4 g = gap_list[gi];
+        for (uint32_t o = threadIdx.x; o < g.y; o += TPB) cell_start[g.x + o] = g.z;
     }
 }
 
@@ -171,7 +179,7 @@ void launch_reorder_cells(const uint32_t* sorted_keys, const uint32_t* perm, con
                           float4* vel_out, float4* force_out, uint32_t* cell_start,
                           uint32_t num_cells, uint32_t n, uint4* gap_list, uint32_t* gap_count,
                           bool with_force, int num_sms, cudaStream_t st) {
-    cudaMemsetAsync(gap_count, 0, sizeof(uint32_t), st);
+    cudaMemsetAsync(gap_count, 0, 2 * sizeof(uint32_t), st);
     const unsigned blocks = blocks_for((uint64_t)n + 1, TPB);
     if (with_force)
         k_reorder_cells<true><<<blocks, TPB, 0, st>>>(sorted_keys, perm, pos_in, vel_in, force_in,

@@ -4,9 +4,6 @@
 
 namespace nprsph {
 
-// longer empty-cell runs of the cell table go to the cooperative fill list (k_fill_gaps)
-constexpr uint32_t GAP_INLINE = 64;
-
 // grid.cu
 void launch_import(const void* aos, float4* posid, float4* velrho, float4* forcep, uint32_t n,
                    cudaStream_t st);
