@@ -175,8 +175,8 @@ class SingleRunner:
         self.sim.set_paused(False)
         st = self.sim.stats()
         self.grid_cells, self.sort_passes = st.num_cells, st.sort_passes
-        # hist + P onesweep + reorder + fill + rho + fused force/integrate
-        self.launches_per_step = 5 + st.sort_passes
+        # hist + P onesweep + reorder + fill + rho + fused force/integrate + their two deferred-queue kernels
+        self.launches_per_step = 7 + st.sort_passes
         self.fused = True
         self._args, self._sph, self._local, self._stream = args, sph, local, stream
         self.parallelism = "1 process, 1 GPU"
@@ -243,8 +243,9 @@ class SlabRunner:
         st = self.grp.sims[0].stats()
         self.grid_cells = (info.x_end - info.x_begin + 2 * st.cell_subdiv) * st.grid_dim[1] * st.grid_dim[2]
         self.sort_passes = int(info.sort_passes)                 # over the occupied x layers only
-        # classify + hist + P onesweep + gather + 2 ghost keys + cells + fill + rho + force + integrate
-        self.launches_per_step = 10 + self.sort_passes
+        # hist + P onesweep + gather/cells + 2 ghost cells + fill + rho + 3 force + integrate/classify
+        # + the 4 deferred-queue kernels
+        self.launches_per_step = 14 + self.sort_passes
         self.fused = False
         self.parallelism = (f"{world} slabs along x, 1 process/GPU, ghost halo (pos; v,rho) + migration "
                             f"via ncclSend/ncclRecv each step")

@@ -12,8 +12,11 @@ namespace nprsph {
 // word per slot pair.
 constexpr uint32_t REC_REACH_MAX = 2;                                  // reach the records support
 constexpr uint32_t REC_COLS = (2 * REC_REACH_MAX + 1) * (2 * REC_REACH_MAX + 1);   // columns per walk
-// words of the record buffer for a capacity of n slots: 4*REC_COLS*ceil(n/2) + ceil(n/2)
-constexpr size_t rec_buffer_words(size_t n) { return (4 * (size_t)REC_COLS + 1) * ((n + 1) / 2); }
+// Behind the records and the control words: the queue of deferred slots (sph_passes.cu "deferred
+// singles"): two counters (density pass, force pass), then up to n slot numbers.
+__host__ __device__ constexpr size_t rec_queue_offset(size_t n) { return ((4 * (size_t)REC_COLS + 1) * ((n + 1) / 2) + 3) & ~(size_t)3; }
+// words of the record buffer for a capacity of n slots
+constexpr size_t rec_buffer_words(size_t n) { return rec_queue_offset(n) + 4 + n; }
 
 // Uniform-grid definition (DESIGN.md "Grid").  The same arithmetic is restated in
 // oracle/sph_oracle.c:oracle_grid_setup / cell_key so keys can be compared bit-exactly.
