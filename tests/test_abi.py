@@ -41,6 +41,51 @@ def test_pod_layouts_match_the_reference_structs(sph):
     assert cfg.pi == pytest.approx(3.141592741)
 
 
+def test_ctypes_mirrors_have_the_c_compilers_layout(sph, tmp_path):
+    """Every struct that crosses the C ABI: size and field offsets as gcc sees include/nprsph.h
+    against the ctypes mirrors the tests and bench.py bind through."""
+    import subprocess
+    from nprsph_b200 import dist as D
+    pairs = {"nprsph_constants": sph.Constants, "nprsph_boundary": sph.Boundary, "nprsph_config": sph.Config,
+             "nprsph_stats": sph.Stats, "nprsph_slider": sph.Slider, "nprsph_collider": sph.Collider,
+             "nprsph_dist_config": D.DistConfig, "nprsph_dist_info": D.DistInfo}
+    rename = {("nprsph_slider", "default"): "def"}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nprsph.h"', 'int main(void) {']
+    for cname, ct in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, *_ in ct._fields_:
+            cf = rename.get((cname, fname), fname)
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {cf}));')
+    lines += ['  printf("nprsph_particle size %zu\\n", sizeof(nprsph_particle));', '  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    seen = {}
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, field, value = line.split()
+        seen[(cname, field)] = int(value)
+    assert seen[("nprsph_particle", "size")] == 64
+    for cname, ct in pairs.items():
+        assert seen[(cname, "size")] == C.sizeof(ct), cname
+        for fname, *_ in ct._fields_:
+            assert seen[(cname, fname)] == getattr(ct, fname).offset, (cname, fname)
+
+
+def test_constants_window_sliders_are_the_references_widgets(sph):
+    """nprsph_slider_info is pure host code: label, range and default of the four ImGui sliders
+    (Main.cpp:242-245; defaults Main.cpp:110-116, the smoothing default 4 lies outside its 7..10)."""
+    lib = sph.load()
+    want = [(b"Mass", 0.01, 0.1, 0.02), (b"Smoothing", 7.0, 10.0, 4.0),
+            (b"Viscosity", 1000.0, 5000.0, 3000.0), (b"Resting Density", 1000.0, 5000.0, 1000.0)]
+    for sid, (label, lo, hi, default) in enumerate(want):
+        s = sph.Slider()
+        assert lib.nprsph_slider_info(sid, C.byref(s)) == sph.OK
+        assert s.label == label
+        assert (s.min, s.max, s.default) == pytest.approx((lo, hi, default))
+    assert lib.nprsph_slider_info(len(want), C.byref(sph.Slider())) != sph.OK
+
+
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
 def test_create_fails_loudly_without_a_gpu(sph):
     with pytest.raises(sph.NprSphError) as ei:
