@@ -100,3 +100,21 @@ def test_nan_onset_matches_reference_text(oracle):
             break
     assert first == int(g["first_nan_step"])
     assert np.array_equal(np.nonzero(np.isnan(P[:, :3]).any(axis=1))[0], g["nan_ids"])
+
+
+def test_collider_extension_matches_its_frozen_fixture(oracle):
+    """tests/golden/colliders.npz (make_colliders.py): 120 steps of a small block flying into a
+    sphere and a box.  Not a pin against the reference (it has no obstacles) but against drift of
+    the repo's own specification: the oracle must reproduce the frozen states bit for bit."""
+    import importlib.util, os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_colliders", os.path.join(here, "make_colliders.py"))
+    mc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mc)
+    fx = np.load(os.path.join(here, "colliders.npz"))
+    p, cols, P = mc.scene()
+    assert np.array_equal(P.view(np.uint32), fx["start"].view(np.uint32))
+    states = mc.run(p, cols, P.copy(), 120)
+    assert np.array_equal(states.view(np.uint32), fx["states"].view(np.uint32))
+    d = np.linalg.norm(states[-1][:, :3].astype(np.float64) - np.array(cols[0][1]), axis=1)
+    assert abs(d.min() / cols[0][2] - 1.0) < 1e-6, "somebody should be sitting on the sphere"
