@@ -47,8 +47,8 @@ float r2_threshold(float h) {
     return t;
 }
 
-// Uniform-grid definition (DESIGN.md "Grid"): cell = h*(1+2^-10)/subdiv, widened when an axis
-// would exceed 2048 cells or the table would exceed max_cells.
+// Uniform-grid definition (DESIGN.md "Grid"): cell = h*(1+2^-14)/subdiv, enlarged when an axis
+// would exceed 16384 cells or the table would exceed max_cells.
 int setup_grid(const nprsph_ctx* c, float h, int slab_ranks, GridDev* g, float* cell_size) {
     int k = c->cfg.cell_subdiv;
     if (!(h > 0.0f) || isinf(h) || k < 1 || k > 4) return -1;
@@ -60,9 +60,12 @@ int setup_grid(const nprsph_ctx* c, float h, int slab_ranks, GridDev* g, float* 
     }
     // slab mode: the cap applies to a rank's share of the table, not to the global grid
     double max_cells = (double)(c->cfg.max_cells ? c->cfg.max_cells : (1u << 28)) * (double)slab_ranks;
-    // cell = base * (1 + widen).  `widen` keeps `reach` cells sufficient under the fp32 rounding of
-    // the cell coordinate (error <= dim * 2^-23 cells): widen >= dim_max * 2^-21, at least 2^-10.
-    double base = (double)h / (double)k, widen = 1.0 / 1024.0, cell = 0.0;
+    // cell = base * (1 + widen), widen = 2^-14.  Two particles closer than h (fp32 predicate, rounding
+    // <= 2^-22 relative) are fewer than `reach` cells apart; the cell coordinate itself is computed in
+    // fp64 (common.cuh:cell_coord, error ~ dim * 2^-52 cells), so the cell size does not have to grow
+    // with the grid.  (An fp32 coordinate needed widen >= dim_max * 2^-21: the cell size then depended
+    // on the box, i.e. on the number of GPUs, and a lattice block slipped against the cells inside it.)
+    double base = (double)h / (double)k, widen = 1.0 / 16384.0, cell = 0.0;
     double dims[3] = {1, 1, 1};
     for (int iter = 0; iter < 64; iter++) {
         cell = base * (1.0 + widen);
@@ -72,13 +75,14 @@ int setup_grid(const nprsph_ctx* c, float h, int slab_ranks, GridDev* g, float* 
             if (dims[a] > dmax) dmax = dims[a];
         }
         if (dmax > 16384.0) { base *= dmax / 16383.0 * 1.0001; continue; }
-        if (dmax / 2097152.0 > widen) { widen *= 2.0; continue; }
         const double total = dims[0] * dims[1] * dims[2];
         if (total > max_cells) { base *= cbrt(total / max_cells) * 1.0001; continue; }
         break;
     }
     for (int a = 0; a < 3; a++) { g->lo[a] = c->bounds.lower[a]; g->dim[a] = (int)dims[a]; }
-    g->inv_cell = (float)(1.0 / cell);
+    g->inv_cell_d = 1.0 / cell;
+    g->inv_cell = (float)g->inv_cell_d;      // fp32 copy: culling coordinates of the walks only
+    g->pad0 = 0;
     g->reach = k;
     g->num_cells = (uint32_t)((int64_t)g->dim[0] * g->dim[1] * g->dim[2]);   // (wraps in slab mode: unused there)
     g->x_off = 0;

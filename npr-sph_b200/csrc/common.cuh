@@ -31,6 +31,8 @@ struct GridDev {
     // global number of x cells.  Single GPU: x_off = 0, dimx_global = dim[0].
     int   x_off;
     int   dimx_global;
+    int   pad0;           // (keeps the struct free of implicit padding: it is compared with memcmp)
+    double inv_cell_d;    // 1 / cell in double: cell coordinates are computed in fp64 (cell_coord)
 };
 
 // Run-time constants of the three passes.  Sources: ConstantsUniform / BoundaryUniform
@@ -57,11 +59,13 @@ struct SphDev {
                         // add.rn.f32x2 into FFMA2 even with explicit rounding modifiers)
 };
 
-__device__ __forceinline__ int cell_coord(float x, float lo, float inv_cell, int dim) {
-    // (x - lo) * inv_cell with two individually rounded operations (no FMA contraction)
-    float u = __fmul_rn(__fsub_rn(x, lo), inv_cell);
-    if (!(u >= 0.0f)) u = 0.0f;
-    const float top = (float)(dim - 1);
+__device__ __forceinline__ int cell_coord(float x, float lo, double inv_cell, int dim) {
+    // (x - lo) * inv_cell in fp64, two individually rounded operations: the error of the cell
+    // coordinate (~ dim * 2^-52 cells) is far below the 2^-14 widening of the cell, so `reach` cells
+    // reach every neighbour whatever the size of the grid, and the cell size does not depend on it
+    double u = __dmul_rn(__dsub_rn((double)x, (double)lo), inv_cell);
+    if (!(u >= 0.0)) u = 0.0;
+    const double top = (double)(dim - 1);
     if (u > top) u = top;
     return (int)u;
 }
@@ -74,7 +78,7 @@ __device__ __forceinline__ bool pos_is_nan(float x, float y, float z) {
 // to the same global cell bit for bit.  May fall outside [0, dim[0]) for a particle that left
 // the slab.
 __device__ __forceinline__ int cell_x_unclamped(float x, const GridDev& g) {
-    return cell_coord(x, g.lo[0], g.inv_cell, g.dimx_global) - g.x_off;
+    return cell_coord(x, g.lo[0], g.inv_cell_d, g.dimx_global) - g.x_off;
 }
 __device__ __forceinline__ int cell_x(float x, const GridDev& g) {
     return min(max(cell_x_unclamped(x, g), 0), g.dim[0] - 1);
@@ -83,8 +87,8 @@ __device__ __forceinline__ int cell_x(float x, const GridDev& g) {
 __device__ __forceinline__ uint32_t cell_key(float x, float y, float z, const GridDev& g) {
     if (pos_is_nan(x, y, z)) return g.num_cells;
     const int cx = cell_x(x, g);
-    const int cy = cell_coord(y, g.lo[1], g.inv_cell, g.dim[1]);
-    const int cz = cell_coord(z, g.lo[2], g.inv_cell, g.dim[2]);
+    const int cy = cell_coord(y, g.lo[1], g.inv_cell_d, g.dim[1]);
+    const int cz = cell_coord(z, g.lo[2], g.inv_cell_d, g.dim[2]);
     return ((uint32_t)cx * (uint32_t)g.dim[1] + (uint32_t)cy) * (uint32_t)g.dim[2] + (uint32_t)cz;
 }
 

@@ -98,8 +98,8 @@ __device__ __forceinline__ uint32_t cell_key_slab(float x, float y, float z, con
     const int cxl = cell_x_unclamped(x, g);
     if (cxl < R) return KEY_GONE_L;
     if (cxl >= R + W) return KEY_GONE_R;
-    const int cy = cell_coord(y, g.lo[1], g.inv_cell, g.dim[1]);
-    const int cz = cell_coord(z, g.lo[2], g.inv_cell, g.dim[2]);
+    const int cy = cell_coord(y, g.lo[1], g.inv_cell_d, g.dim[1]);
+    const int cz = cell_coord(z, g.lo[2], g.inv_cell_d, g.dim[2]);
     return ((uint32_t)cxl * (uint32_t)g.dim[1] + (uint32_t)cy) * (uint32_t)g.dim[2] + (uint32_t)cz;
 }
 

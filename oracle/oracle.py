@@ -46,6 +46,7 @@ class Grid(C.Structure):
     _fields_ = [
         ("lo", C.c_float * 3), ("inv_cell", C.c_float), ("dim", C.c_int32 * 3),
         ("reach", C.c_int32), ("num_cells", C.c_uint32), ("cell_size", C.c_float),
+        ("inv_cell_d", C.c_double),
     ]
 
 

@@ -345,9 +345,11 @@ int oracle_grid_setup(const oracle_params* p, int k, uint32_t max_cells, oracle_
         ext[a] = e > 0.0 ? e : 0.0;
     }
     if (max_cells == 0) max_cells = 1u << 28;
-    /* cell = base * (1 + widen); widen >= dim_max * 2^-21 (at least 2^-10) keeps `reach` cells
-     * sufficient under the fp32 rounding of the cell coordinate (DESIGN.md "Grid") */
-    double base = (double)h / (double)k, widen = 1.0 / 1024.0, cell = 0.0;
+    /* cell = base * (1 + widen), widen = 2^-14: two particles closer than h (fp32 predicate, rounding
+     * <= 2^-22 relative) are fewer than `reach` cells apart, and the cell coordinate is computed in
+     * fp64 (error ~ dim * 2^-52 cells), so `reach` cells suffice for any grid size
+     * (DESIGN.md "Grid") */
+    double base = (double)h / (double)k, widen = 1.0 / 16384.0, cell = 0.0;
     double dims[3] = {1, 1, 1};
     for (int iter = 0; iter < 64; iter++) {
         cell = base * (1.0 + widen);
@@ -357,32 +359,33 @@ int oracle_grid_setup(const oracle_params* p, int k, uint32_t max_cells, oracle_
             if (dims[a] > dmax) dmax = dims[a];
         }
         if (dmax > 16384.0) { base *= dmax / 16383.0 * 1.0001; continue; }
-        if (dmax / 2097152.0 > widen) { widen *= 2.0; continue; }
         double total = dims[0] * dims[1] * dims[2];
         if (total > (double)max_cells) { base *= cbrt(total / (double)max_cells) * 1.0001; continue; }
         break;
     }
     for (int a = 0; a < 3; a++) { g->lo[a] = p->lower[a]; g->dim[a] = (int32_t)dims[a]; }
-    g->inv_cell = (float)(1.0 / cell);
+    g->inv_cell_d = 1.0 / cell;
+    g->inv_cell = (float)g->inv_cell_d;
     g->cell_size = (float)cell;
     g->reach = k;
     g->num_cells = (uint32_t)(g->dim[0] * (int64_t)g->dim[1] * g->dim[2]);
     return 0;
 }
 
-static inline int cell_coord(float x, float lo, float inv_cell, int dim) {
-    float u = (x - lo) * inv_cell;
-    if (!(u >= 0.0f)) u = 0.0f;
-    float top = (float)(dim - 1);
+static inline int cell_coord(float x, float lo, double inv_cell, int dim) {
+    double d = (double)x - (double)lo;
+    double u = d * inv_cell;
+    if (!(u >= 0.0)) u = 0.0;
+    double top = (double)(dim - 1);
     if (u > top) u = top;
     return (int)u;
 }
 
 static inline uint32_t cell_key(const float* pos, const oracle_grid* g) {
     if (pos[0] != pos[0] || pos[1] != pos[1] || pos[2] != pos[2]) return g->num_cells;
-    int cx = cell_coord(pos[0], g->lo[0], g->inv_cell, g->dim[0]);
-    int cy = cell_coord(pos[1], g->lo[1], g->inv_cell, g->dim[1]);
-    int cz = cell_coord(pos[2], g->lo[2], g->inv_cell, g->dim[2]);
+    int cx = cell_coord(pos[0], g->lo[0], g->inv_cell_d, g->dim[0]);
+    int cy = cell_coord(pos[1], g->lo[1], g->inv_cell_d, g->dim[1]);
+    int cz = cell_coord(pos[2], g->lo[2], g->inv_cell_d, g->dim[2]);
     return ((uint32_t)cx * (uint32_t)g->dim[1] + (uint32_t)cy) * (uint32_t)g->dim[2] + (uint32_t)cz;
 }
 

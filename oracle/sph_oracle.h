@@ -58,6 +58,7 @@ typedef struct oracle_grid {
     int32_t reach;          /* cells to walk each side (= cell_subdiv) */
     uint32_t num_cells;     /* sentinel key for NaN positions == num_cells */
     float cell_size;
+    double inv_cell_d;      /* 1 / cell in double: the cell coordinate is computed in fp64 */
 } oracle_grid;
 
 void oracle_default_params(oracle_params* p);

@@ -153,6 +153,20 @@ def test_dam_break_small_free_running(sph, oracle, cell_subdiv):
     print(f"\n[drift] cell_subdiv={cell_subdiv}: max |x_gpu - x_oracle| / h after 200 steps = {drift:.3e}")
 
 
+def test_long_axis_far_from_the_origin(sph, oracle):
+    """A 16000-cell axis with the fluid 80 m from the grid origin: cell keys / permutation / cell
+    table and neighbour counts still match the oracle bit for bit (the cell coordinate is fp64 on
+    both sides; the cell size no longer grows with the grid), fields to the usual tolerance."""
+    p = oracle.dam_break_params(12, 14, 10)
+    p.lower[0], p.upper[0] = -40.0, 40.0
+    P = oracle.jitter(oracle.make_block(12, 14, 10), 0.4 * 0.005, seed=13)
+    P[:, 0] += np.float32(39.9)
+    sim = make_sim(sph, p, cell_subdiv=2)
+    for _ in range(3):
+        check_passes(sim, sph, oracle, P, p, 2)
+    assert sim.stats().grid_dim[0] > 14000
+
+
 def test_iterated_permutation_every_step(sph, oracle):
     """Slot permutation == iterated stable sort of the oracle's keys, checked on every step."""
     nx, ny, nz = 12, 20, 10

@@ -49,6 +49,31 @@ def test_grid_variant_is_bit_identical_to_all_pairs(oracle, cell_subdiv):
         assert np.array_equal(A, B, equal_nan=True)
 
 
+@pytest.mark.parametrize("cell_subdiv", [1, 2])
+def test_reach_suffices_on_a_16000_cell_axis(oracle, cell_subdiv):
+    """The cell is only 2^-14 wider than h / subdiv and the cell coordinate is computed in fp64, so
+    `reach` cells must still reach every neighbour when an axis holds ~16000 cells and the fluid
+    sits 80 m from the grid origin (fp32 positions there have a 4e-6 ulp, 1/1250 of the spacing):
+    the grid variant stays bit-identical to the all-pairs loops."""
+    p = oracle.dam_break_params(10, 12, 8)
+    p.lower[0], p.upper[0] = -40.0, 40.0
+    g = oracle.grid_setup(p, cell_subdiv)
+    assert g.dim[0] > 7000 * cell_subdiv
+    A = oracle.jitter(oracle.make_block(10, 12, 8), 0.4 * 0.005, seed=9)
+    A[:, 0] += np.float32(39.9)
+    B = A.copy()
+    for _ in range(3):
+        ca = oracle.pass_rho(A, p, counts=True)
+        cb = oracle.pass_rho(B, p, counts=True, grid=cell_subdiv)
+        assert np.array_equal(ca, cb) and ca.min() > 5
+        ca = oracle.pass_force(A, p, counts=True)
+        cb = oracle.pass_force(B, p, counts=True, grid=cell_subdiv)
+        assert np.array_equal(ca, cb)
+        oracle.pass_integrate(A, p)
+        oracle.pass_integrate(B, p)
+        assert np.array_equal(A, B, equal_nan=True)
+
+
 def test_r2_threshold_is_the_sqrt_predicate(oracle):
     """(sqrtf(r2) < h) == (r2 < T) for every fp32 r2 around the threshold."""
     for h in (0.02, 0.01, 0.0125, 0.035, 1.0, 3e-5, 7.5):
