@@ -464,7 +464,7 @@ static PhaseTrace g_trace;
 // Everything between "positions + unsorted slab keys of the own particles are final" and "cell
 // table and ghosts are ready for k_rho", for all local ranks in lock step.
 int prepare_group(nprsph_ctx** cs, int n) {
-    Xfer x[64];
+    Xfer x[64] = {};
     g_trace.begin(cs, n);
     // (1) classify + counter exchange, one host sync
     for (int r = 0; r < n; r++) {
@@ -628,7 +628,7 @@ int ensure_prepared(nprsph_ctx** cs, int n) {
 // ev (nullable): 5 events recorded on rank 0's stream at the stage boundaries
 // [prepare | rho | halo(v,rho) | force | integrate]
 int step_group(nprsph_ctx** cs, int n, cudaEvent_t* ev = nullptr) {
-    Xfer x[64];
+    Xfer x[64] = {};
     if (ev) CK(cs[0], cudaEventRecord(ev[0], cs[0]->stream));
     int rc = ensure_prepared(cs, n);
     if (rc) return rc;
