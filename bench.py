@@ -6,9 +6,15 @@
 
 One "step" = one pass of the hot path (grid maintenance + rho/pressure + force + integrate,
 i.e. display()'s compute block, Main.cpp:291-305) over every particle of the workload.
-Workload: the 16,777,216-particle fp32 dam break (BASELINE.json configs[2], the configuration
-the HBM-roofline headline is quoted on), 256^3 lattice block, stable parameter recipe of
-SURVEY.md 8(d), seeded jitter.  Prints ONE JSON line (rank 0).
+
+Workload (N = 1): the 16,777,216-particle fp32 dam break (BASELINE.json configs[2], the
+configuration the HBM-roofline headline is quoted on), 256^3 lattice block, seeded jitter, timed
+AFTER the dam has broken (--evolve-steps, default 2000): a real, disordered fluid.  The same
+kernels on the still-standing lattice (the friendliest arrangement) are reported under "lattice".
+N > 1: ONE global dam break of 16 Mi particles per GPU split into x slabs (weak scaling), after a
+parity check of the NCCL path against a single-GPU run ("dist_parity"); BASELINE configs[3] (64 Mi
+strong scaling) and configs[4] (32 Mi per GPU, migration every step) are timed in the same run
+under "configs".  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -27,27 +33,47 @@ if ROOT not in sys.path:
 
 METRIC = "SPH particle-updates/s (rho+force+integrate)"
 UNIT = "particle-updates/s"
-# algorithmic (compulsory) bytes per particle per launch, SURVEY.md 8(d) / DESIGN.md
+SPACING = 0.005
+JITTER, SEED = 1e-4 * SPACING, 1234
+# algorithmic (compulsory) bytes per particle per launch, SURVEY.md 8(d) / DESIGN.md 4.  The fused
+# force+integrate launch reads pos+vel+(rho,p) once (48) and writes force (16) and pos+vel (32).
 ALGO_BYTES = {"rho": 32, "force": 64, "integrate": 96}
-KERNEL_OF_STAGE = {"rho": "k_rho", "force": "k_force", "integrate": "k_integrate",
+ALGO_BYTES_FUSED = {"rho": 32, "force": 96}
+KERNEL_OF_STAGE = {"rho": "k_rho", "force": "k_force_records", "integrate": "k_integrate",
                    "sort": "k_onesweep(+k_radix_hist)", "reorder": "k_reorder_cells(+k_fill_gaps)",
                    "keys": "k_keys"}
+# SASS-counted issue slots of the density pass per distance test (one candidate against one target):
+# 40 instructions per two candidates per target pair (profiles/r2_sass_k_rho_loop.txt)
+RHO_INSTR_PER_TEST = 10.0
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=256, help="lattice block is side^3 particles per GPU")
-    ap.add_argument("--subdiv", type=int, default=2, help="grid cells per smoothing length")
+    ap.add_argument("--subdiv", type=int, default=0, help="grid cells per smoothing length (0 = automatic: 2 here)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--evolve-steps", type=int, default=2000,
-                    help="N = 1: afterwards let the dam break run this many steps and time the step again on "
-                         "the disordered fluid (reported under \"disordered\"; 0 = skip)")
+                    help="steps the dam break runs before the timed region (0 = time the standing lattice)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1 main line: weak = side^3 per GPU; strong = BASELINE configs[3], 512x256x512 in total")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the secondary BASELINE configs[3]/[4] sections")
+    ap.add_argument("--extra-evolve-steps", type=int, default=600)
+    ap.add_argument("--rebalance-every", type=int, default=8,
+                    help="N > 1: slab faces may move one x layer every so many steps (0 = static slabs)")
     return ap.parse_args()
+
+
+def workload_name(dims, evolve_steps, n_gpus):
+    nx, ny, nz = dims
+    state = f"timed after {evolve_steps} steps of dam break" if evolve_steps else "standing lattice"
+    return (f"dam_break_fp32 block {nx}x{ny}x{nz} = {nx * ny * nz} particles on {n_gpus} GPU(s), h=2s, "
+            f"recipe npr-sph_b200/scenes.py (gas_const 2000), jitter seed {SEED}, {state}")
 
 
 def peaks():
@@ -166,24 +192,24 @@ def relaunch_under_torchrun(args):
 
 # ------------------------------------------------------------------------------------------------
 class SingleRunner:
-    """N = 1: one context, the plain C-ABI calls (nprsph_step / upload / download)."""
+    """N = 1: one context, the plain C-ABI calls (nprsph_step / upload_state / download_positions)."""
 
-    def __init__(self, sph, O, args, local, stream):
-        side = args.side
-        self.n_own = side ** 3
-        self.p = O.dam_break_params(side, side, side)
-        self.sim = sph.Simulation(device=local, stream=stream.cuda_stream, cell_subdiv=args.subdiv)
+    def __init__(self, sph, dims, args, local, stream, flags=0):
+        self.dims = dims
+        self.n_own = self.n_total = dims[0] * dims[1] * dims[2]
+        self.p = sph.scenes.dam_break_params(*dims)
+        self.sim = sph.Simulation(device=local, stream=stream.cuda_stream, cell_subdiv=args.subdiv, flags=flags)
         self.sim.apply_params(self.p)
-        self.sim.scene_block(side, side, side, 0.005, None, 1e-4 * 0.005, 1234)
+        self.sim.scene_block(*dims, SPACING, None, JITTER, SEED)
         self.sim.set_paused(False)
         st = self.sim.stats()
-        self.grid_cells, self.sort_passes = st.num_cells, st.sort_passes
+        self.grid_cells, self.sort_passes, self.subdiv = st.num_cells, st.sort_passes, st.cell_subdiv
         # hist + P onesweep + reorder + fill + rho + fused force/integrate + their two deferred-queue kernels
         self.launches_per_step = 7 + st.sort_passes
-        self.fused = True
-        self._args, self._sph, self._local, self._stream = args, sph, local, stream
+        self.fused = not (flags & sph.FLAG_NO_FUSE)
         self.parallelism = "1 process, 1 GPU"
-        self.api = "nprsph_upload_particles + nprsph_step(1) + nprsph_download_particles, pinned host buffers"
+        self.api = ("nprsph_upload_state (pos+vel, 32 B/particle) + nprsph_step(1) + nprsph_download_positions "
+                    "(16 B/particle, asynchronous), pinned host buffers")
 
     def step(self, k):
         self.sim.step(k)
@@ -191,67 +217,46 @@ class SingleRunner:
     def profile(self, k):
         return self.sim.profile_step(k)
 
-    def profile_passes(self, k):
-        """Per-pass times of the three-launch form of the step (FLAG_NO_FUSE) on a second context
-        carrying the same state, so that every pass keeps its own roofline line."""
-        side = self._args.side
-        sim = self._sph.Simulation(device=self._local, stream=self._stream.cuda_stream,
-                                   cell_subdiv=self._args.subdiv, flags=self._sph.FLAG_NO_FUSE)
-        sim.apply_params(self.p)
-        sim.scene_block(side, side, side, 0.005, None, 1e-4 * 0.005, 1234)
-        sim.set_paused(False)
-        sim.step(5)
-        prof = sim.profile_step(k)
-        sim.close()
-        return prof
+    def nan_particles(self):
+        return int(self.sim.stats().nan_particles)
 
-    def alloc_host(self, torch):
-        n = self.n_own
-        self.h = [torch.empty(n * 16, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.sim.download_ptr(self.h[0].data_ptr(), n)
-
-    def e2e_step(self, i):
-        src, dst = self.h[i % 2], self.h[(i + 1) % 2]
-        self.sim.upload_ptr(src.data_ptr(), self.n_own)
-        self.sim.step(1)
-        self.sim.download_ptr(dst.data_ptr(), self.n_own)
-        return self.n_own * 64, self.n_own * 64, self.n_own
-
-    def last_host_state(self, i):
-        return self.h[i % 2].numpy().reshape(self.n_own, 16)
+    def close(self):
+        self.sim.close()
 
 
 class SlabRunner:
-    """N > 1: ONE global dam break (side*N x side x side particles) split into x slabs, one rank
-    per GPU, ghost halo exchange + migration over NCCL send/recv every step."""
+    """N > 1: ONE global dam break split into x slabs, one rank per GPU, ghost halo exchange +
+    migration over NCCL send/recv every step, slab faces re-balanced as the fluid moves."""
 
-    def __init__(self, sph, O, args, rank, local, world, stream, torch, dist):
+    def __init__(self, sph, dims, args, rank, local, world, stream, torch, dist):
         from nprsph_b200.dist import SlabGroup, unique_id
-        side = args.side
-        self.world = world
-        self.p = O.dam_break_params(side * world, side, side)
+        self.dims, self.world = dims, world
+        self.n_total = dims[0] * dims[1] * dims[2]
+        self.p = sph.scenes.dam_break_params(*dims)
         idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         self.grp = SlabGroup.nccl(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local,
-                                  stream=stream.cuda_stream, cell_subdiv=args.subdiv)
+                                  stream=stream.cuda_stream, cell_subdiv=args.subdiv,
+                                  rebalance_every=args.rebalance_every)
         self.grp.apply_params(self.p)
-        self.grp.scene_block(side * world, side, side, 0.005, None, 1e-4 * 0.005, 1234)
+        self.grp.scene_block(*dims, SPACING, None, JITTER, SEED)
         self.grp.set_paused(False)
         self.grp.step(1)                       # distributes the scene; part of the warm-up
         info = self.grp.info()
         self.n_own = int(info.num_own)
         self.cap = int(info.cap_own)
         st = self.grp.sims[0].stats()
+        self.subdiv = st.cell_subdiv
         self.grid_cells = (info.x_end - info.x_begin + 2 * st.cell_subdiv) * st.grid_dim[1] * st.grid_dim[2]
         self.sort_passes = int(info.sort_passes)                 # over the occupied x layers only
-        # hist + P onesweep + gather/cells + 2 ghost cells + fill + rho + 3 force + integrate/classify
-        # + the 4 deferred-queue kernels
+        # hist + P onesweep + gather/cells + 2 ghost cells + fill + rho (+deferred) + 3 x (fused force/integrate
+        # + deferred) + counter set
         self.launches_per_step = 14 + self.sort_passes
-        self.fused = False
+        self.fused = True
         self.parallelism = (f"{world} slabs along x, 1 process/GPU, ghost halo (pos; v,rho) + migration "
-                            f"via ncclSend/ncclRecv each step")
+                            f"via ncclSend/ncclRecv each step, faces re-balanced every {args.rebalance_every} steps")
         self.api = "nprsph_dist_upload + nprsph_dist_step(1) + nprsph_dist_download, pinned host buffers"
 
     def step(self, k):
@@ -260,28 +265,90 @@ class SlabRunner:
     def profile(self, k):
         return self.grp.profile_step(k)
 
-    def alloc_host(self, torch):
-        self.h = [torch.empty(self.cap * 16, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.hid = [torch.empty(self.cap, dtype=torch.int32).pin_memory() for _ in range(2)]
-        self.n_host = self.grp.download_ptr(0, self.h[0].data_ptr(), self.hid[0].data_ptr(), self.cap)
+    def nan_particles(self):
+        return int(self.grp.info().nan_particles)
 
-    def e2e_step(self, i):
-        a, b = i % 2, (i + 1) % 2
-        n_in = self.n_host
-        self.grp.upload_ptr(0, self.h[a].data_ptr(), self.hid[a].data_ptr(), n_in)
-        self.grp.step(1)
-        self.n_host = self.grp.download_ptr(0, self.h[b].data_ptr(), self.hid[b].data_ptr(), self.cap)
-        return n_in * 68, self.n_host * 68, n_in
+    def close(self):
+        self.grp.close()
 
-    def last_host_state(self, i):
-        return self.h[i % 2].numpy().reshape(self.cap, 16)[:self.n_host]
+
+def timed(run, stream, torch, steps, warm, barrier, max_over_ranks, sampler=None):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run.step(max(warm, 3))
+    barrier()
+    if sampler:
+        sampler.mark()
+    e0.record(stream)
+    run.step(steps)
+    e1.record(stream)
+    barrier()
+    if sampler:
+        sampler.mark()
+    return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+
+def dist_parity(sph, rank, local, world, stream, torch, dist):
+    """The slab-decomposed step over real NCCL against a single-context run of the same scene: a
+    flow that pushes particles through every slab face (migration, ghosts, re-balancing)."""
+    import numpy as np
+    from nprsph_b200.dist import SlabGroup, unique_id
+    nx, ny, nz, steps = 96, 32, 24, 100
+    p = sph.scenes.dam_break_params(nx, ny, nz)
+    p.gravity[0] = 300.0
+    idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    grp = SlabGroup.nccl(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local,
+                         stream=stream.cuda_stream, cell_subdiv=2, rebalance_every=4)
+    grp.apply_params(p)
+    grp.scene_block(nx, ny, nz, SPACING, None, 2e-4, 21)
+    grp.set_paused(False)
+    grp.step(steps)
+    rec, ids = grp.download()
+    info = grp.info()
+    mine = {"rec": rec, "ids": ids, "migrated": int(info.migrated_total), "rebalanced": int(info.rebalanced),
+            "ghosts": int(info.ghosts_left + info.ghosts_right)}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    grp.close()
+    if rank != 0:
+        return None
+    ref = sph.Simulation(device=local, stream=stream.cuda_stream, cell_subdiv=2)
+    ref.apply_params(p)
+    ref.scene_block(nx, ny, nz, SPACING, None, 2e-4, 21)
+    ref.set_paused(False)
+    ref.step(steps)
+    want = ref.download()
+    ref.close()
+    n = nx * ny * nz
+    got = np.full((n, 16), np.nan, np.float32)
+    seen = np.zeros(n, np.int32)
+    for g in gathered:
+        seen[g["ids"]] += 1
+        got[g["ids"]] = g["rec"]
+    partition = bool((seen == 1).all())
+    out = {"scene": f"{nx}x{ny}x{nz} block, g_x = 300, {steps} steps, NCCL send/recv, re-balancing every 4 steps "
+                    f"vs nprsph_step on one context", "ranks": world, "ids_partition_exactly": partition,
+           "migrated": sum(g["migrated"] for g in gathered), "ghosts": sum(g["ghosts"] for g in gathered),
+           "face_moves": sum(g["rebalanced"] for g in gathered), "tolerance": 1e-5, "max_rel": {}}
+    ok = partition and out["migrated"] > 0 and out["ghosts"] > 0
+    for name, cols in (("pos", slice(0, 3)), ("vel", slice(4, 7)), ("force", slice(8, 11)), ("rho", slice(12, 13))):
+        a, b = got[:, cols].astype(np.float64), want[:, cols].astype(np.float64)
+        same_nan = bool(np.array_equal(np.isnan(a), np.isnan(b)))
+        m = ~np.isnan(b)
+        rel = float(np.abs(a[m] - b[m]).max() / max(np.abs(b[m]).max(), 1e-300)) if same_nan and m.any() else float("inf")
+        out["max_rel"][name] = rel
+        ok = ok and same_nan and rel <= 1e-5
+    out["ok"] = bool(ok)
+    return out
 
 
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import nprsph_b200 as sph
-    from oracle import oracle as O   # only for the parameter recipe and the cpu_baseline leg
 
     rank, local, world = dist_env()
     if args.gpus > 1 and world == 1:
@@ -296,45 +363,76 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     stream = torch.cuda.Stream(device=local)
-    if world == 1:
-        run = SingleRunner(sph, O, args, local, stream)
-    else:
-        run = SlabRunner(sph, O, args, rank, local, world, stream, torch, dist)
-    n_total = args.side ** 3 * world
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(v):
+    def reduce(v, op):
         t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(ms):
+        return reduce(ms, dist.ReduceOp.MAX) if world > 1 else float(ms)
+
+    def sum_over_ranks(v):
+        return reduce(v, dist.ReduceOp.SUM) if world > 1 else float(v)
+
+    def make_runner(dims):
+        if world == 1:
+            return SingleRunner(sph, dims, args, local, stream)
+        return SlabRunner(sph, dims, args, rank, local, world, stream, torch, dist)
+
+    def slab_report(run, steps_timed, moved_before):
+        """own min/max over ranks, hand-overs per step in the timed window, face moves so far"""
+        if world == 1:
+            return None
+        info = run.grp.info()
+        own = int(info.num_own)
+        return {"own_min": int(reduce(own, dist.ReduceOp.MIN)), "own_max": int(reduce(own, dist.ReduceOp.MAX)),
+                "migrated_per_step": (sum_over_ranks(int(info.migrated_total)) - moved_before) / max(steps_timed, 1),
+                "face_moves_total": int(sum_over_ranks(int(info.rebalanced))),
+                "nan_particles": int(sum_over_ranks(int(info.nan_particles)))}
+
+    def moved_so_far(run):
+        return sum_over_ranks(int(run.grp.info().migrated_total)) if world > 1 else 0.0
+
+    parity = None
+    if world > 1:
+        parity = dist_parity(sph, rank, local, world, stream, torch, dist)
+
+    # ---- main line ---------------------------------------------------------------------------
+    side = args.side
+    if world > 1 and args.scaling == "strong":
+        dims, scaling = (512, 256, 512), "strong"                      # BASELINE configs[3]
+    else:
+        dims, scaling = (side * world, side, side), "weak"
+    run = make_runner(dims)
+    n_total = run.n_total
     warm = max(args.warmup, 3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    peak, peak_src = peaks()
+
+    lattice = None
+    if args.evolve_steps > 0:          # the standing lattice first (secondary figure), then let the dam break
+        ms_l = timed(run, stream, torch, min(args.steps, 20), warm, barrier, max_over_ranks)
+        prof_l = run.profile(3)
+        lattice = {"ms_per_step": round(ms_l, 4), "value": n_total / (ms_l * 1e-3), "unit": UNIT,
+                   "per_kernel_ms": {k: round(v, 4) for k, v in prof_l.items()},
+                   "step_frac": round(192 * n_total / world / (ms_l * 1e-3) / 1e9 / peak, 4),
+                   "note": "the same scene before the dam breaks: every warp walks identical columns (the "
+                           "friendliest arrangement; round 1's headline)"}
+        run.step(args.evolve_steps)
     sampler = ClockSampler(local)
     sampler.start()                    # nvidia-smi needs ~0.1 s to deliver its first sample
-    run.step(warm)
-    barrier()
-    sampler.mark()
-    e0.record(stream)
-    run.step(args.steps)
-    e1.record(stream)
-    barrier()
-    sampler.mark()
+    moved0 = moved_so_far(run)
+    ms_per_step = timed(run, stream, torch, args.steps, warm, barrier, max_over_ranks, sampler)
     clocks = sampler.stop()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = ms_total / args.steps
-    value = n_total * args.steps / (ms_total * 1e-3)
+    value = n_total / (ms_per_step * 1e-3)
+    slab = slab_report(run, args.steps + warm, moved0)
+    nan_main = run.nan_particles() if world == 1 else slab["nan_particles"]
 
     # per-kernel device times (CUDA events between stages on the same stream), live
     prof = run.profile(max(3, min(args.steps, 10)))
@@ -346,23 +444,30 @@ def run_ours(args):
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
         per_rank = gathered
-    # N = 1: nprsph_step runs force + integrate as ONE launch (booked under "force"); its
-    # algorithmic bytes are those of the two passes it performs, 64 + 96.
-    algo = dict(ALGO_BYTES)
+    # nprsph_step runs force + integrate as ONE launch (booked under "force")
+    algo = dict(ALGO_BYTES_FUSED if run.fused else ALGO_BYTES)
     kernel_of = dict(KERNEL_OF_STAGE)
-    passes = None
     if run.fused:
-        algo = {"rho": 32, "force": 64 + 96}
         kernel_of["force"] = "k_force_records<FUSE> (force + integrate passes in one launch)"
-        passes = run.profile_passes(max(3, min(args.steps, 10)))
+    walk = passes = None
+    if world == 1:
+        walk = run.sim.walk_stats()
+        # per-pass times of the three-launch form on a second context carrying the same evolved state
+        host = np.empty((run.n_own, 16), np.float32)
+        run.sim.download(host)
+        nofuse = SingleRunner(sph, dims, args, local, stream, flags=sph.FLAG_NO_FUSE)
+        nofuse.sim.upload(host)
+        nofuse.sim.step(3)
+        passes = nofuse.profile(max(3, min(args.steps, 10)))
+        nofuse.close()
+        del host
     stage = max(algo, key=lambda k: prof[k])
-    peak, peak_src = peaks()
     achieved = algo[stage] * n_k / (prof[stage] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(f"{kernel_of[stage].split()[0]}@{n_k}@subdiv{args.subdiv}")
+            traffic = json.load(f).get(f"{kernel_of[stage].split()[0]}@{n_k}@subdiv{run.subdiv}")
     roofline = {"kernel": kernel_of[stage], "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src,
@@ -380,86 +485,208 @@ def run_ours(args):
                     "note": "same state, FLAG_NO_FUSE: k_rho, k_force_records, k_integrate as separate launches"},
                 "note": "rho/force are instruction-issue bound (DESIGN.md 4); frac is algorithmic "
                         "bytes / time / measured HBM peak, rank 0"}
+    if walk:
+        # second figure of SURVEY 8(d): the neighbour passes in their own unit
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        t_rho = prof["rho"] * 1e-3
+        tests_s = walk["distance_tests"] / t_rho
+        issue_peak = 148 * 4 * sm_hz                          # warp instructions / s
+        roofline["issue"] = {
+            "distance_tests_per_step": walk["distance_tests"], "neighbours_per_particle": round(walk["neighbours"] / n_k, 2),
+            "tests_per_particle": round(walk["distance_tests"] / n_k, 1), "columns_per_pair_walk": round(walk["columns"] / max(walk["pair_walks"] + walk["single_walks"], 1), 2),
+            "unpaired_slots": walk["single_walks"],
+            "k_rho_pair_tests_per_s": tests_s,
+            "fp32_issue_peak_warp_inst_per_s": issue_peak,
+            "k_rho_frac_of_issue_peak_spent_on_tests": round(tests_s * RHO_INSTR_PER_TEST / 32 / issue_peak, 4),
+            "note": f"{RHO_INSTR_PER_TEST:.0f} issue slots per distance test (SASS count), 148 SMs x 4 schedulers x SM clock"}
 
-    # end to end through the C ABI with HOST buffers: upload -> step -> download, every step
-    run.alloc_host(torch)
-    run.e2e_step(0)
-    barrier()
-    e0.record(stream)
-    h2d = d2h = 0
-    for i in range(1, args.e2e_steps + 1):
-        a, b, _ = run.e2e_step(i)
-        h2d, d2h = h2d + a, d2h + b
-    e1.record(stream)
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    # ---- end to end through the C ABI with HOST buffers, every step -----------------------------
+    if world == 1:
+        n = run.n_own
+        host = torch.empty(n * 16, dtype=torch.float32).pin_memory()
+        run.sim.download_ptr(host.data_ptr(), n)
+        rec = host.view(n, 16)
+        hin = [(torch.empty(n * 4, dtype=torch.float32).pin_memory(), torch.empty(n * 4, dtype=torch.float32).pin_memory())
+               for _ in range(2)]
+        for hp, hv in hin:
+            hp.view(n, 4).copy_(rec[:, 0:4]); hv.view(n, 4).copy_(rec[:, 4:8])
+        hout = [torch.empty(n * 4, dtype=torch.float32).pin_memory() for _ in range(2)]
+
+        def e2e_step(i):
+            hp, hv = hin[i % 2]
+            run.sim.upload_state_ptr(hp.data_ptr(), hv.data_ptr(), n)
+            run.sim.step(1)
+            run.sim.download_positions_ptr(hout[i % 2].data_ptr(), n, asynchronous=True)
+            return n * 32, n * 16
+        e2e_step(0)
+        run.sim.sync()
+        barrier()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for i in range(1, args.e2e_steps + 1):
+            a, b = e2e_step(i)
+            h2d, d2h = h2d + a, d2h + b
+        run.sim.sync()                      # the last asynchronous download has landed
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        moved = float(np.nanmax(np.abs(hout[args.e2e_steps % 2].view(n, 4)[:, :3].numpy() - rec[:, 0:3].numpy())))
+        assert 0.0 < moved < 0.1, f"e2e: downloaded positions are not one step away from the uploaded ones ({moved})"
+        e2e_note = ("host wall clock around upload_state -> step -> asynchronous download_positions of every step, "
+                    "final sync inside; the result of step i leaves while the inputs of step i+1 arrive")
+    else:
+        cap = run.cap
+        h = [torch.empty(cap * 16, dtype=torch.float32).pin_memory() for _ in range(2)]
+        hid = [torch.empty(cap, dtype=torch.int32).pin_memory() for _ in range(2)]
+        state = {"n": run.grp.download_ptr(0, h[0].data_ptr(), hid[0].data_ptr(), cap)}
+
+        def e2e_step(i):
+            a, b = i % 2, (i + 1) % 2
+            n_in = state["n"]
+            run.grp.upload_ptr(0, h[a].data_ptr(), hid[a].data_ptr(), n_in)
+            run.grp.step(1)
+            state["n"] = run.grp.download_ptr(0, h[b].data_ptr(), hid[b].data_ptr(), cap)
+            return n_in * 68, state["n"] * 68
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for i in range(1, args.e2e_steps + 1):
+            a, b = e2e_step(i)
+            h2d, d2h = h2d + a, d2h + b
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        e2e_note = "host wall clock, upload -> step -> download of every rank's records, barrier on both sides"
+    e2e_ms = max_over_ranks(e2e_ms)
     e2e = {"value": n_total * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(sum_over_ranks(h2d) / args.e2e_steps),
            "d2h_bytes_per_step": int(sum_over_ranks(d2h) / args.e2e_steps),
-           "steps": args.e2e_steps, "api": run.api}
+           "steps": args.e2e_steps, "api": run.api, "timing": e2e_note}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import numpy as np
-        host = np.ascontiguousarray(run.last_host_state(args.e2e_steps + 1))   # carries rho/p
-        cpu_baseline = cpu_sample(O, host, run.p, budget_s=12.0)
+        cpu_baseline = cpu_baselines(np.ascontiguousarray(rec.numpy()), run.p, run.subdiv)
+    main_workload = workload_name(dims, args.evolve_steps, world)
+    run.close()
+    if world == 1:
+        del host, hin, hout, rec
+    else:
+        del h, hid
+    torch.cuda.empty_cache()
 
-    # The timed region above still sees the initial lattice (warm-up + steps are ~100 steps).  A real
-    # fluid is disordered: the same scene a few thousand steps later, same metric, same kernels.
-    disordered = None
-    if world == 1 and args.evolve_steps > 0:
-        run.step(args.evolve_steps)
-        k = 20
-        run.step(3)
-        e0.record(stream)
-        run.step(k)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / k
-        prof_d = run.profile(5)
-        disordered = {"evolved_steps": args.evolve_steps + args.steps + warm, "ms_per_step": round(ms, 4),
-                      "value": n_total / (ms * 1e-3), "unit": UNIT,
-                      "per_kernel_ms": {k_: round(v, 4) for k_, v in prof_d.items()},
-                      "nan_particles": int(run.sim.stats().nan_particles),
-                      "note": "same scene and kernels after the dam has broken: lanes of a warp no longer "
-                              "walk identical columns (DESIGN.md 4, Disordered arrangements)"}
+    # ---- BASELINE configs[3] (64 Mi strong scaling) and configs[4] (32 Mi per GPU weak scaling) ----
+    configs = None
+    if not args.no_extra_configs:
+        configs = {}
+        for name, cdims, kind in (("config4_strong_64Mi", (512, 256, 512), "strong"),
+                                  ("config5_weak_32Mi_per_gpu", (256 * world, 256, 512), "weak")):
+            if cdims == dims:
+                configs[name] = {"same_as": "main line"}
+                continue
+            r = make_runner(cdims)
+            r.step(args.extra_evolve_steps)
+            m0 = moved_so_far(r)
+            k = max(5, min(args.steps, 20))
+            ms = timed(r, stream, torch, k, 3, barrier, max_over_ranks)
+            configs[name] = {"workload": workload_name(cdims, args.extra_evolve_steps, world), "scaling": kind,
+                             "particles_total": r.n_total, "ms_per_step": round(ms, 4),
+                             "value": r.n_total / (ms * 1e-3), "unit": UNIT, "steps": k,
+                             "step_frac": round(192 * r.n_total / world / (ms * 1e-3) / 1e9 / peak, 4),
+                             "slab": slab_report(r, k + 3, m0),
+                             "nan_particles": r.nan_particles() if world == 1 else None}
+            r.close()
+            torch.cuda.empty_cache()
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": f"dam_break_{args.side ** 3}_per_gpu_fp32 (block {args.side * world}x"
-                                      f"{args.side}x{args.side}, h=2s, stable recipe SURVEY 8(d), jitter seed 1234)",
-                          "particles_total": n_total, "cell_subdiv": args.subdiv,
+               "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": main_workload,
+                          "particles_total": n_total, "cell_subdiv": int(run.subdiv),
                           "grid_cells_per_rank": int(run.grid_cells), "sort_passes": int(run.sort_passes),
-                          "parallelism": run.parallelism,
+                          "parallelism": run.parallelism, "nan_particles": nan_main,
                           "l2": "working set per step (>2 GB per GPU) exceeds the 126 MB L2; no flush needed"},
                "roofline": roofline, "e2e": e2e, "gpu_launches": run.launches_per_step * args.steps,
                "clocks": clocks}
         if cpu_baseline:
             out["cpu_baseline"] = cpu_baseline
-        if disordered:
-            out["disordered"] = disordered
+        if lattice:
+            out["lattice"] = lattice
+        if slab:
+            out["slab"] = slab
+        if parity is not None:
+            out["dist_parity"] = parity
+        if configs:
+            out["configs"] = configs
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_sample(O, host, p, budget_s):
+# ---- CPU legs (the only places bench.py touches oracle/) ------------------------------------------
+def oracle_params(O, p):
+    q = O.default_params()
+    for k in ("mass", "smoothing_coeff", "visc", "resting_rho", "particle_radius", "gas_const", "damping", "dt", "pi"):
+        setattr(q, k, getattr(p, k))
+    for a in range(3):
+        q.gravity[a] = p.gravity[a]
+    for a in range(4):
+        q.upper[a], q.lower[a] = p.upper[a], p.lower[a]
+    return q
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def all_pairs_sample(O, host, q, budget_s):
     """Reference algorithm (all-pairs j loop, the shaders' own) for a bounded sample of the
     workload's particles on this box's host cores.  `host` already carries rho/p."""
     import numpy as np
     n = len(host)
     threads = O.num_threads()
     idx0 = np.linspace(0, n - 1, threads, dtype=np.int32)
-    t0 = time.perf_counter(); O.sample_update(host, p, idx0); dt0 = time.perf_counter() - t0
+    t0 = time.perf_counter(); O.sample_update(host, q, idx0); dt0 = time.perf_counter() - t0
     m = int(max(threads, min(4096, budget_s / max(dt0, 1e-6) * threads)))
     m -= m % threads
     idx = np.linspace(0, n - 1, m, dtype=np.int32)
-    t0 = time.perf_counter(); O.sample_update(host, p, idx); dt = time.perf_counter() - t0
-    return {"value": m / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"oracle all-pairs update (rho+force+integrate, the reference's O(N) loop per "
-                      f"particle) of {m} evenly spaced particles out of {n}, {dt:.1f} s"}
+    t0 = time.perf_counter(); O.sample_update(host, q, idx); dt = time.perf_counter() - t0
+    return m / dt, m, dt
+
+
+def cpu_baselines(host, p, subdiv):
+    """Three CPU figures on this box's own cores: the reference's all-pairs algorithm on
+    a bounded sample of the workload (`value`), the same UNIFORM-GRID algorithm as the GPU path on the
+    whole workload (oracle_step_grid, bit-identical to all-pairs), and BASELINE configs[0] -- the
+    reference's default 10,000-particle scene stepped by the OpenMP transcription of the shaders."""
+    import numpy as np
+    from oracle import oracle as O
+    q = oracle_params(O, p)
+    threads, n = O.num_threads(), len(host)
+    v, m, dt = all_pairs_sample(O, host, q, budget_s=8.0)
+    out = {"value": v, "unit": UNIT, "cores": threads, "cpu": cpu_model(), "kind": "port",
+           "sample": f"oracle all-pairs update (rho+force+integrate, the reference's O(N) loop per "
+                     f"particle) of {m} evenly spaced particles out of {n}, {dt:.1f} s"}
+    G = host.copy()
+    t0 = time.perf_counter(); O.step(G, q, 1, grid=int(subdiv)); dtg = time.perf_counter() - t0
+    out["uniform_grid_same_algorithm"] = {
+        "value": n / dtg, "unit": UNIT, "cores": threads, "steps": 1, "seconds": round(dtg, 2),
+        "what": f"oracle_step_grid (cell = h/{subdiv}, the GPU path's neighbour search restated in C + OpenMP) over all {n} particles"}
+    del G
+    P = O.make_block(10, 100, 10)
+    qd = O.default_params()
+    O.step(P, qd, 3)
+    k = 30
+    t0 = time.perf_counter(); O.step(P, qd, k); dtc = time.perf_counter() - t0
+    out["config1_default_scene_openmp"] = {
+        "value": 10000 * k / dtc, "unit": UNIT, "cores": threads, "steps": k, "ms_per_step": round(dtc / k * 1e3, 3),
+        "what": "BASELINE configs[0]: 10 x 100 x 10 block, the reference's constants, all-pairs OpenMP transcription (oracle_step)"}
+    return out
 
 
 def run_reference(args):
@@ -469,37 +696,45 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 in its workers; the reference arm gets every host core
+    if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import numpy as np
+    import nprsph_b200 as sph           # parameter recipe only (no CUDA call)
     from oracle import oracle as O
-    side = args.side
-    n = side ** 3
-    p = O.dam_break_params(side, side, side)
-    host = O.jitter(O.make_block(side, side, side), 1e-4 * 0.005, 1234)
+    side, gpus = args.side, max(args.gpus, 1)
+    dims = (512, 256, 512) if gpus > 1 and args.scaling == "strong" else (side * gpus, side, side)
+    n = dims[0] * dims[1] * dims[2]
+    p = sph.scenes.dam_break_params(*dims)
+    q = oracle_params(O, p)
+    host = O.jitter(O.make_block(*dims), JITTER, SEED)
     host[:, 12] = p.resting_rho          # rho_j read by the force loop (timing only)
     threads = O.num_threads()
     steps, warm = args.steps, max(args.warmup, 1)
     idx0 = np.linspace(0, n - 1, threads, dtype=np.int32)
-    t0 = time.perf_counter(); O.sample_update(host, p, idx0); dt0 = time.perf_counter() - t0
+    t0 = time.perf_counter(); O.sample_update(host, q, idx0); dt0 = time.perf_counter() - t0
     per_step = min(6.0, 150.0 / (steps + warm))
     m = int(max(threads, per_step / max(dt0, 1e-6) * threads))
     m -= m % threads
     idx = np.linspace(0, n - 1, m, dtype=np.int32)
     for _ in range(warm):
-        O.sample_update(host, p, idx)
+        O.sample_update(host, q, idx)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.sample_update(host, p, idx)
+        O.sample_update(host, q, idx)
     dt = time.perf_counter() - t0
     value = m * steps / dt
     sample = (f"{m} evenly spaced particles of the {n}-particle dam break per step, all-pairs "
-              f"rho+force+integrate (oracle/sph_oracle.c), {threads} OpenMP threads")
+              f"rho+force+integrate (oracle/sph_oracle.c), {threads} OpenMP threads on {cpu_model()}; the all-pairs "
+              f"cost does not depend on the arrangement, so the block is not evolved first")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"dam_break_{n}_per_gpu_fp32 (side {side}, h=2s, stable recipe SURVEY 8(d), "
-                               f"jitter seed 1234)", "particles_total": n, "algorithm": "all-pairs (reference)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "scaling": "strong" if dims == (512, 256, 512) and gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(dims, args.evolve_steps, gpus), "particles_total": n,
+                   "algorithm": "all-pairs (reference)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "cpu": cpu_model(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NPRSPH_ABI_VERSION 1
+#define NPRSPH_ABI_VERSION 2
 
 typedef enum nprsph_status {
     NPRSPH_OK = 0,
@@ -155,6 +155,19 @@ int nprsph_download_particles(nprsph_ctx* ctx, nprsph_particle* host, uint64_t n
  * valid until the next call that changes n; brought up to date by this call */
 int nprsph_device_particles(nprsph_ctx* ctx, void** device_ptr, uint64_t* n);
 uint64_t nprsph_num_particles(const nprsph_ctx* ctx);
+/* Streaming interface (new; the reference keeps the state on the GPU for ever).
+ * upload_state: the INPUTS of a step for the n existing particles, original order: pos4 / vel4 are
+ *   n float4 each (xyz used; the records' .w lanes keep their values).  Force, density and pressure
+ *   are outputs of the passes and read as zero until the next step.  Asynchronous on the context's
+ *   stream; host buffers must stay valid until nprsph_sync() (use pinned memory to overlap).
+ * download_positions: what the renderer reads -- attribute 0 = the vec4 at offset 0 of each record
+ *   (Main.cpp:533-535, toon_vs.glsl:17) -- n float4 in original order, 16 B per particle instead of
+ *   64.  With NPRSPH_DOWNLOAD_ASYNC the copy runs on a separate stream behind the work queued so
+ *   far and the call returns at once: the result leaves while the next step's inputs arrive and
+ *   the next step computes; nprsph_sync() waits for it. */
+#define NPRSPH_DOWNLOAD_ASYNC 1u
+int nprsph_upload_state(nprsph_ctx* ctx, const float* pos4, const float* vel4, uint64_t n);
+int nprsph_download_positions(nprsph_ctx* ctx, float* pos4, uint64_t n, uint32_t flags);
 
 /* ---- pause / reset (keyboard(), Main.cpp:454-476) ---------------------------------------- */
 int nprsph_set_paused(nprsph_ctx* ctx, int paused);
@@ -178,6 +191,10 @@ int nprsph_get_stats(nprsph_ctx* ctx, nprsph_stats* out);
  * stage_ms[NPRSPH_NUM_STAGES] receives the mean ms per step of each stage */
 int nprsph_profile_step(nprsph_ctx* ctx, int n_steps, float* stage_ms);
 int nprsph_debug_read(nprsph_ctx* ctx, int item, void* host_dst, uint64_t bytes);
+/* work of one density pass over the current arrangement (the unit the two issue-bound neighbour
+ * kernels are measured in): out = {distance tests (target x candidate), non-empty
+ * columns walked, pair walks, single-target walks, neighbours found incl. self} */
+int nprsph_walk_stats(nprsph_ctx* ctx, uint64_t out[5]);
 /* stand-alone run of the onesweep sort on host arrays (tests): stable, low key_bits bits */
 int nprsph_sort_pairs_host(int device, const uint32_t* keys_in, const uint32_t* vals_in,
                            uint64_t n, int key_bits, uint32_t* keys_out, uint32_t* vals_out);
@@ -243,6 +260,9 @@ typedef struct nprsph_dist_config {
     uint64_t max_own;           /* capacities in particles; 0 = derived from the scene */
     uint64_t max_ghost;         /* per side */
     uint64_t max_migrate;       /* per side and step */
+    int32_t  rebalance_every;   /* > 0: every so many steps each interior slab face may move by one x
+                                   cell layer towards the lighter rank (0 = static slabs) */
+    int32_t  reserved;
 } nprsph_dist_config;
 
 typedef struct nprsph_dist_info {
@@ -251,11 +271,23 @@ typedef struct nprsph_dist_info {
     uint64_t num_own, ghosts_left, ghosts_right, nan_particles;
     uint64_t migrated_total, steps_done, cap_own, cap_ghost;
     uint32_t sort_bits, sort_passes;   /* key bits / digit passes of the last step's slab sort */
+    uint64_t rebalanced;        /* slab-face moves of this rank so far (re-balancing) */
+    uint32_t last_migrated;     /* particles handed to the neighbours in the last step */
+    uint32_t reserved;
 } nprsph_dist_info;
 
 /* count-balanced slab boundaries from a per-x-plane particle histogram (pure host code):
  * bounds[0] = 0 <= ... <= bounds[world] = dimx, every slab at least min_width cells wide */
 int nprsph_slab_partition(const uint64_t* hist, int dimx, int world, int min_width, int32_t* bounds);
+/* Re-balancing decision for ONE slab face (pure host code, the rule nprsph_dist_step applies every
+ * rebalance_every steps).  a / b = the per-step counter blocks of the rank left / right of the face,
+ * NPRSPH_SLAB_COUNTER_WORDS words each: both ranks hold both blocks after the step's counter
+ * exchange, so they decide alike without further communication.  Returns -1 (the face moves one x
+ * cell layer to the left: a hands its last layer to b), +1 (b hands its first layer to a) or 0. */
+#define NPRSPH_SLAB_COUNTER_WORDS 12
+enum { NPRSPH_CNT_LEAVE_L = 0, NPRSPH_CNT_LEAVE_R, NPRSPH_CNT_HALO_L, NPRSPH_CNT_HALO_R, NPRSPH_CNT_NAN,
+       NPRSPH_CNT_XMAX, NPRSPH_CNT_OWN, NPRSPH_CNT_FREE, NPRSPH_CNT_WIDTH, NPRSPH_CNT_CAP_MIGRATE };
+int nprsph_slab_face_move(const uint32_t* a, const uint32_t* b, int reach, uint32_t cap_ghost);
 int nprsph_dist_unique_id(uint8_t id[128]);
 int nprsph_dist_init(nprsph_ctx* ctx, const nprsph_dist_config* cfg);
 int nprsph_dist_link_local(nprsph_ctx** ranks, int n);
@@ -265,11 +297,12 @@ int nprsph_dist_scene_block(nprsph_ctx* ctx, int nx, int ny, int nz, float spaci
                             const float origin[3], float jitter, uint32_t seed);
 /* collective step.  NCCL: ranks = {ctx}, n_local = 1.  LOCAL: all ranks in rank order. */
 int nprsph_dist_step(nprsph_ctx** ranks, int n_local, int steps);
-/* collective; copies the own particles of ranks[which] (records + their global indices) */
+/* copies the particles ranks[which] holds (records + their global indices); every particle is held
+ * by exactly one rank at any time.  Collective only right after nprsph_dist_scene_block(). */
 int nprsph_dist_download(nprsph_ctx** ranks, int n_local, int which, nprsph_particle* records,
                          uint32_t* ids, uint64_t capacity, uint64_t* n_out);
 /* replaces the own particles of this rank by host records + global indices (restart / e2e);
- * records whose position lies outside the rank's slab are dropped */
+ * a record whose position lies in the slab next door is handed over by the next step */
 int nprsph_dist_upload(nprsph_ctx* ctx, const nprsph_particle* records, const uint32_t* ids, uint64_t n);
 /* collective nprsph_profile_step(): SORT = whole prepare phase, REORDER = (v, rho) halo exchange */
 int nprsph_dist_profile_step(nprsph_ctx** ranks, int n_local, int steps, float* stage_ms);

@@ -6,3 +6,4 @@ The directory is named `npr-sph_b200`; import it as `nprsph_b200` (root-level sh
 """
 from .binding import *  # noqa: F401,F403
 from . import binding  # noqa: F401
+from . import scenes  # noqa: F401

@@ -20,6 +20,7 @@ ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED, ERR_COMM = -1, -2,
 FLAG_COUNT_NEIGHBOURS = 1
 FLAG_NO_HITMASK = 2
 FLAG_NO_FUSE = 4
+DOWNLOAD_ASYNC = 1
 
 STAGES = ("keys", "sort", "cells", "reorder", "rho", "force", "integrate")
 DBG_SORTED_KEYS, DBG_SLOT_IDS, DBG_CELL_START, DBG_COUNTS_RHO, DBG_COUNTS_FORCE, DBG_LAST_PERM = range(6)
@@ -92,6 +93,9 @@ SYMBOLS = {
     "nprsph_upload_particles": (C.c_int, [_P, _P, C.c_uint64]),
     "nprsph_download_particles": (C.c_int, [_P, _P, C.c_uint64]),
     "nprsph_device_particles": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "nprsph_upload_state": (C.c_int, [_P, _P, _P, C.c_uint64]),
+    "nprsph_download_positions": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32]),
+    "nprsph_walk_stats": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "nprsph_num_particles": (C.c_uint64, [_P]),
     "nprsph_set_paused": (C.c_int, [_P, C.c_int]),
     "nprsph_toggle_pause": (C.c_int, [_P]),
@@ -115,6 +119,7 @@ SYMBOLS = {
     # multi-GPU (slab decomposition); the Python-side driver lives in dist.py
     "nprsph_slab_partition": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
                                         C.POINTER(C.c_int32)]),
+    "nprsph_slab_face_move": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.c_uint32]),
     "nprsph_dist_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "nprsph_dist_init": (C.c_int, [_P, _P]),
     "nprsph_dist_link_local": (C.c_int, [C.POINTER(_P), C.c_int]),
@@ -304,6 +309,33 @@ class Simulation:
 
     def download_ptr(self, host_ptr: int, n: int):
         self._ck(self.lib.nprsph_download_particles(self._h, host_ptr, n))
+
+    def upload_state(self, pos4: np.ndarray, vel4: np.ndarray):
+        """The inputs of a step (positions, velocities; (n, 4) float32 each, original order)."""
+        p, v = np.ascontiguousarray(pos4, np.float32), np.ascontiguousarray(vel4, np.float32)
+        assert p.shape == v.shape == (self.num_particles, 4)
+        self._ck(self.lib.nprsph_upload_state(self._h, p.ctypes.data, v.ctypes.data, len(p)))
+        self.sync()                     # the numpy temporaries must outlive the copies
+
+    def upload_state_ptr(self, pos_ptr: int, vel_ptr: int, n: int):
+        self._ck(self.lib.nprsph_upload_state(self._h, pos_ptr, vel_ptr, n))
+
+    def download_positions(self, out: np.ndarray | None = None) -> np.ndarray:
+        """(n, 4) float32: the vec4 at offset 0 of every record, original order."""
+        n = self.num_particles
+        if out is None:
+            out = np.empty((n, 4), np.float32)
+        assert out.flags.c_contiguous and out.nbytes == n * 16
+        self._ck(self.lib.nprsph_download_positions(self._h, out.ctypes.data, n, 0))
+        return out
+
+    def download_positions_ptr(self, host_ptr: int, n: int, asynchronous: bool = False):
+        self._ck(self.lib.nprsph_download_positions(self._h, host_ptr, n, DOWNLOAD_ASYNC if asynchronous else 0))
+
+    def walk_stats(self) -> dict:
+        out = (C.c_uint64 * 5)()
+        self._ck(self.lib.nprsph_walk_stats(self._h, out))
+        return dict(zip(("distance_tests", "columns", "pair_walks", "single_walks", "neighbours"), map(int, out)))
 
     def device_particles(self):
         p, n = _P(), C.c_uint64()

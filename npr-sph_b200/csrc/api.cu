@@ -50,7 +50,7 @@ float r2_threshold(float h) {
 // Uniform-grid definition (DESIGN.md "Grid"): cell = h*(1+2^-14)/subdiv, enlarged when an axis
 // would exceed 16384 cells or the table would exceed max_cells.
 int setup_grid(const nprsph_ctx* c, float h, int slab_ranks, GridDev* g, float* cell_size) {
-    int k = c->cfg.cell_subdiv;
+    int k = effective_subdiv(c);
     if (!(h > 0.0f) || isinf(h) || k < 1 || k > 4) return -1;
     double ext[3];
     for (int a = 0; a < 3; a++) {
@@ -92,6 +92,29 @@ int setup_grid(const nprsph_ctx* c, float h, int slab_ranks, GridDev* g, float* 
 }
 
 }  // namespace
+
+// cell_subdiv 0 = automatic: the reference's block sits on a lattice of spacing PARTICLE_RADIUS
+// (make_grid, Main.cpp:488-505) and h = smoothing_coeff * PARTICLE_RADIUS (rho_pres_comp.glsl:40), so
+// cell = h / round(smoothing_coeff) holds about one particle: 4 at the reference's default, 2 for the
+// h = 2s dam break.  Columns of a walk then stay within the 16 hit bits of a pair record.
+int nprsph::effective_subdiv(const nprsph_ctx* c) {
+    if (c->cfg.cell_subdiv > 0) return c->cfg.cell_subdiv;
+    const float k = roundf(c->consts.smoothing_coeff);
+    return k >= 4.0f ? 4 : k >= 1.0f ? (int)k : 1;
+}
+
+int nprsph::ensure_records(nprsph_ctx* c, uint64_t slots, int reach) {
+    size_t need = 0;
+    if (!(c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) && slots && records_fit(reach, slots))
+        need = rec_buffer_words(slots, rec_cols_of(reach));
+    if (need == c->hitmask_words) return NPRSPH_OK;
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->hitmask_words = 0;
+    CK(c, realloc_dev(c->hitmask, need));
+    c->hitmask_words = need;
+    c->mask_valid = false;
+    return NPRSPH_OK;
+}
 
 int nprsph::refresh_params(nprsph_ctx* c) {
     if (!c->params_dirty) return NPRSPH_OK;
@@ -147,6 +170,10 @@ int nprsph::refresh_params(nprsph_ctx* c) {
         CK(c, cudaMalloc(&c->gap_list, gaps * sizeof(uint4)));
         c->gap_cap = gaps;
     }
+    if (!c->dist) {              // slab mode sizes its records in alloc_slab
+        int rc = ensure_records(c, c->cap, g.reach);
+        if (rc) return rc;
+    }
     c->grid = g;
     c->sph = s;
     c->cell_size = cell_size;
@@ -177,8 +204,8 @@ int ensure_capacity(nprsph_ctx* c, uint64_t n) {
         CK(c, realloc_dev(c->counts_force, n));
     }
     { char* w = (char*)c->sort_ws; CK(c, realloc_dev(w, sort_workspace_bytes(n))); c->sort_ws = w; }
-    // (column descriptors hold 27-bit slots: beyond that the force pass re-tests its candidates)
-    CK(c, realloc_dev(c->hitmask, (c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) || n > (1u << 27) ? (size_t)0 : rec_buffer_words(n)));
+    c->hitmask_words = 0;       // sized with the grid (refresh_params -> ensure_records)
+    CK(c, realloc_dev(c->hitmask, (size_t)0));
     c->cap = n;
     c->params_dirty = true;     // gap-list capacity depends on cap
     return NPRSPH_OK;
@@ -285,6 +312,7 @@ int publish(nprsph_ctx* c) {
 // after the AoS buffer was (re)written by upload or a scene kernel
 int adopt_aos(nprsph_ctx* c) {
     c->cur = 0;
+    c->gl_seeded = false;          // every lane of the records may have changed
     launch_import(c->aos, c->pos[0], c->vel[0], c->frc[0], (uint32_t)c->n, c->stream);
     CK(c, cudaGetLastError());
     c->keys_valid = false;
@@ -367,7 +395,7 @@ void nprsph_config_default(nprsph_config* cfg) {
     cfg->damping = 0.3f;
     cfg->dt = 1.0f / 10000.0f;
     cfg->pi = 3.141592741f;
-    cfg->cell_subdiv = 1;
+    cfg->cell_subdiv = 0;       // automatic: effective_subdiv()
     cfg->max_cells = 0;
     cfg->flags = 0;
 }
@@ -394,7 +422,6 @@ int nprsph_create(const nprsph_config* cfg, nprsph_ctx** out) {
     nprsph_ctx* c = new (std::nothrow) nprsph_ctx();
     if (!c) return fail(nullptr, NPRSPH_ERR_NOMEM, "out of host memory%s");
     c->cfg = *cfg;
-    if (c->cfg.cell_subdiv == 0) c->cfg.cell_subdiv = 1;
     c->num_sms = prop.multiProcessorCount;
     // ConstantsData / BoundaryData defaults, Main.cpp:110-122
     c->consts = {0.02f, 4.0f, 3000.0f, 1000.0f};
@@ -426,6 +453,13 @@ int nprsph_destroy(nprsph_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->gl_res) cudaGraphicsUnregisterResource(c->gl_res);
     if (c->dist) dist_destroy(c);
+    if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
+    if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); }
+    for (int i = 0; i < nprsph_ctx::STAGE_CHUNKS; i++) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    for (int i = 0; i < 2; i++) { if (c->ev_imported[i]) cudaEventDestroy(c->ev_imported[i]); cudaFree(c->stage_in[i]); }
+    if (c->ev_published) cudaEventDestroy(c->ev_published);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    cudaFree(c->stage_pos);
     cudaFree(c->aos);
     for (int b = 0; b < 2; b++) {
         cudaFree(c->pos[b]); cudaFree(c->vel[b]); cudaFree(c->frc[b]);
@@ -531,7 +565,6 @@ int nprsph_set_config(nprsph_ctx* c, const nprsph_config* cfg) {
     if (cfg->flags != c->cfg.flags)
         return fail(c, NPRSPH_ERR_INVALID, "flags are fixed at create time%s");
     c->cfg = *cfg;
-    if (c->cfg.cell_subdiv == 0) c->cfg.cell_subdiv = 1;
     c->params_dirty = true;
     return NPRSPH_OK;
 }
@@ -589,6 +622,117 @@ int nprsph_device_particles(nprsph_ctx* c, void** device_ptr, uint64_t* n) {
     return NPRSPH_OK;
 }
 
+// ---- streaming interface ---------------------------------------------------------------------------
+// The reference uploads the particle buffer once and never reads it back; a host application that
+// feeds state in (restart, emitters, a coupled solver) and draws the result needs two things per
+// frame: the INPUTS of a step (positions and velocities -- force, density and pressure are outputs of
+// the passes) and the positions the renderer consumes (attribute 0, Main.cpp:533-535).
+static int ensure_staging(nprsph_ctx* c) {
+    if (!c->h2d_stream) {
+        CK(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        CK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < nprsph_ctx::STAGE_CHUNKS; i++) CK(c, cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) CK(c, cudaEventCreateWithFlags(&c->ev_imported[i], cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_published, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
+    }
+    if (c->stage_cap < c->n) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaStreamSynchronize(c->h2d_stream));
+        CK(c, cudaStreamSynchronize(c->d2h_stream));
+        c->stage_cap = 0;
+        for (int i = 0; i < 2; i++) CK(c, realloc_dev(c->stage_in[i], 2 * c->n));
+        CK(c, realloc_dev(c->stage_pos, c->n));
+        c->stage_cap = c->n;
+        // fresh events: nothing recorded yet counts as complete
+    }
+    return NPRSPH_OK;
+}
+
+int nprsph_upload_state(nprsph_ctx* c, const float* pos4, const float* vel4, uint64_t n) {
+    GUARD(c);
+    SINGLE_ONLY(c);
+    if (n != c->n) return fail(c, NPRSPH_ERR_INVALID, "upload_state replaces the state of the existing particles: n must equal "
+                               "nprsph_num_particles() (nprsph_upload_particles changes the count)%s");
+    if (!n) return NPRSPH_OK;
+    if (!pos4 || !vel4) return fail(c, NPRSPH_ERR_INVALID, "null host buffer%s");
+    int rc = ensure_staging(c);
+    if (rc) return rc;
+    // Chunked: the copy stream brings chunk k+1 in while the context's stream converts chunk k into
+    // the working arrays; the staging buffers alternate between calls, so this call's copies may run
+    // while the previous step still computes.
+    const int b = c->stage_cur;
+    c->stage_cur ^= 1;
+    float4* sp = c->stage_in[b];
+    float4* sv = sp + n;
+    CK(c, cudaStreamWaitEvent(c->h2d_stream, c->ev_imported[b], 0));     // its last import has read the buffer
+    const uint64_t per = (n + nprsph_ctx::STAGE_CHUNKS - 1) / nprsph_ctx::STAGE_CHUNKS;
+    for (int k = 0; k < nprsph_ctx::STAGE_CHUNKS; k++) {
+        const uint64_t first = (uint64_t)k * per;
+        if (first >= n) break;
+        const uint64_t cnt = n - first < per ? n - first : per;
+        CK(c, cudaMemcpyAsync(sp + first, pos4 + 4 * first, cnt * sizeof(float4), cudaMemcpyHostToDevice, c->h2d_stream));
+        CK(c, cudaMemcpyAsync(sv + first, vel4 + 4 * first, cnt * sizeof(float4), cudaMemcpyHostToDevice, c->h2d_stream));
+        CK(c, cudaEventRecord(c->ev_chunk[k], c->h2d_stream));
+        CK(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0));
+        launch_import_state(sp + first, sv + first, (uint32_t)first, (uint32_t)cnt, c->pos[0], c->vel[0], c->frc[0], c->stream);
+    }
+    CK(c, cudaEventRecord(c->ev_imported[b], c->stream));
+    CK(c, cudaGetLastError());
+    c->cur = 0;
+    c->keys_valid = false;
+    c->grid_valid = false;
+    c->mask_valid = false;
+    c->sorted_keys = nullptr;
+    c->aos_stale = true;           // the records' pos / vel lanes follow at the next publish
+    return NPRSPH_OK;
+}
+
+int nprsph_download_positions(nprsph_ctx* c, float* pos4, uint64_t n, uint32_t flags) {
+    GUARD(c);
+    SINGLE_ONLY(c);
+    if (n > c->n) return fail(c, NPRSPH_ERR_INVALID, "download larger than the particle buffer%s");
+    if (n && !pos4) return fail(c, NPRSPH_ERR_INVALID, "null host buffer%s");
+    if (!n) return NPRSPH_OK;
+    int rc = ensure_staging(c);
+    if (rc) return rc;
+    if (c->d2h_pending) CK(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));    // the previous copy has left the staging buffer
+    launch_publish_positions(c->pos[c->cur], c->aos, c->stage_pos, (uint32_t)c->n, c->stream);
+    CK(c, cudaEventRecord(c->ev_published, c->stream));
+    CK(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_published, 0));
+    CK(c, cudaMemcpyAsync(pos4, c->stage_pos, n * sizeof(float4), cudaMemcpyDeviceToHost, c->d2h_stream));
+    CK(c, cudaEventRecord(c->ev_copied, c->d2h_stream));
+    c->d2h_pending = true;
+    if (!(flags & NPRSPH_DOWNLOAD_ASYNC)) {
+        CK(c, cudaStreamSynchronize(c->d2h_stream));
+        c->d2h_pending = false;
+    }
+    return NPRSPH_OK;
+}
+
+int nprsph_walk_stats(nprsph_ctx* c, uint64_t out[5]) {
+    GUARD(c);
+    SINGLE_ONLY(c);
+    if (!out) return NPRSPH_ERR_INVALID;
+    for (int i = 0; i < 5; i++) out[i] = 0;
+    if (c->n == 0) return NPRSPH_OK;
+    int rc = ensure_grid(c, true, nullptr);
+    if (rc) return rc;
+    unsigned long long* d_out = nullptr;
+    CK(c, cudaMalloc(&d_out, 5 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_out, 0, 5 * sizeof(unsigned long long), c->stream);
+    if (e == cudaSuccess) {
+        launch_walk_stats(c->pos[c->cur], c->cell_start, 0u, (uint32_t)c->n, c->grid, c->sph, d_out, c->stream);
+        unsigned long long h[5];
+        e = cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) for (int i = 0; i < 5; i++) out[i] = h[i];
+    }
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(c, NPRSPH_ERR_CUDA, "walk_stats: %s", cudaGetErrorString(e));
+    return NPRSPH_OK;
+}
+
 uint64_t nprsph_num_particles(const nprsph_ctx* c) { return c ? c->n : 0; }
 
 // ---- pause / reset ---------------------------------------------------------------------------------
@@ -637,6 +781,8 @@ int nprsph_step(nprsph_ctx* c, int n_steps) {
 int nprsph_sync(nprsph_ctx* c) {
     GUARD(c);
     CK(c, cudaStreamSynchronize(c->stream));
+    if (c->d2h_stream) CK(c, cudaStreamSynchronize(c->d2h_stream));     // asynchronous position downloads
+    c->d2h_pending = false;
     return NPRSPH_OK;
 }
 
@@ -697,7 +843,7 @@ int nprsph_get_stats(nprsph_ctx* c, nprsph_stats* out) {
     out->cell_size = c->cell_size;
     out->smoothing_length = c->sph.h;
     out->paused = c->paused ? 1 : 0;
-    out->cell_subdiv = c->cfg.cell_subdiv;
+    out->cell_subdiv = effective_subdiv(c);
     return NPRSPH_OK;
 }
 
@@ -740,7 +886,7 @@ int nprsph_debug_read(nprsph_ctx* c, int item, void* dst, uint64_t bytes) {
     if (item == NPRSPH_DBG_RECORD_CTL) {           // control word of every slot pair (also in slab mode)
         const uint64_t half = (c->cap + 1) / 2;
         if (!dst || !c->hitmask || bytes != half * 4) return fail(c, NPRSPH_ERR_INVALID, "record control words: need ceil(capacity/2)*4 bytes and the column records%s");
-        CK(c, cudaMemcpyAsync(dst, c->hitmask + (size_t)4 * REC_COLS * half, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(dst, c->hitmask + (size_t)4 * rec_cols_of(c->grid.reach) * half, bytes, cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
         return NPRSPH_OK;
     }
@@ -864,7 +1010,7 @@ int nprsph_snapshot_save(nprsph_ctx* c, const char* path) {
         h.particle_radius = c->cfg.particle_radius; h.gas_const = c->cfg.gas_const;
         for (int a = 0; a < 3; a++) h.gravity[a] = c->cfg.gravity[a];
         h.damping = c->cfg.damping; h.dt = c->cfg.dt; h.pi = c->cfg.pi;
-        h.cell_subdiv = c->cfg.cell_subdiv; h.paused = c->paused ? 1 : 0;
+        h.cell_subdiv = effective_subdiv(c); h.paused = c->paused ? 1 : 0;
         memcpy(raw, &h, sizeof h);
         f = fopen(path, "wb");
         if (!f || fwrite(raw, 1, 256, f) != 256 || fwrite(ids, 4, n, f) != n ||
@@ -949,14 +1095,28 @@ int nprsph_gl_publish(nprsph_ctx* c) {
     GUARD(c);
     SINGLE_ONLY(c);
     if (!c->gl_res) return fail(c, NPRSPH_ERR_STATE, "no GL buffer registered%s");
-    int rc = publish(c);
-    if (rc) return rc;
+    // The first publish after a register / upload / reset seeds every lane of the GL buffer from the
+    // record array (the .w lanes and extras[2..3] the passes never write, Appendix B-9).  After that
+    // the renderer's buffer is updated IN PLACE: the publish kernel scatters the lanes the passes
+    // write (pos/vel/force .xyz, rho, pressure) from the cell-ordered state straight into the mapped
+    // buffer, in original particle order (the brush pass is order-dependent, Main.cpp:355-360).
+    if (!c->gl_seeded) {
+        int rc = publish(c);
+        if (rc) return rc;
+    }
     CK(c, cudaGraphicsMapResources(1, &c->gl_res, c->stream));
     void* p = nullptr; size_t sz = 0;
     cudaError_t e = cudaGraphicsResourceGetMappedPointer(&p, &sz, c->gl_res);
     if (e == cudaSuccess && sz < c->n * sizeof(nprsph_particle)) e = cudaErrorInvalidValue;
-    if (e == cudaSuccess && c->n)
-        e = cudaMemcpyAsync(p, c->aos, c->n * sizeof(nprsph_particle), cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess && c->n) {
+        if (!c->gl_seeded) {
+            e = cudaMemcpyAsync(p, c->aos, c->n * sizeof(nprsph_particle), cudaMemcpyDeviceToDevice, c->stream);
+            c->gl_seeded = e == cudaSuccess;
+        } else {
+            launch_publish(c->pos[c->cur], c->vel[c->cur], c->frc[c->cur], p, (uint32_t)c->n, c->stream);
+            e = cudaGetLastError();
+        }
+    }
     cudaGraphicsUnmapResources(1, &c->gl_res, c->stream);
     if (e != cudaSuccess) return fail(c, NPRSPH_ERR_CUDA, "gl_publish: %s", cudaGetErrorString(e));
     return NPRSPH_OK;
@@ -967,6 +1127,7 @@ int nprsph_gl_unregister(nprsph_ctx* c) {
     if (!c->gl_res) return NPRSPH_OK;
     CK(c, cudaGraphicsUnregisterResource(c->gl_res));
     c->gl_res = nullptr;
+    c->gl_seeded = false;
     return NPRSPH_OK;
 }
 

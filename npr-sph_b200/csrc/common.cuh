@@ -9,14 +9,17 @@ namespace nprsph {
 
 // Column records handed from the density pass to the force pass (sph_passes.cu "column records"):
 // one 64-bit record per non-empty column of a walk, two record planes per slot pair, one control
-// word per slot pair.
-constexpr uint32_t REC_REACH_MAX = 2;                                  // reach the records support
-constexpr uint32_t REC_COLS = (2 * REC_REACH_MAX + 1) * (2 * REC_REACH_MAX + 1);   // columns per walk
+// word per slot pair.  A walk visits at most (2*reach+1)^2 columns; the buffer is laid out for the
+// reach of the current grid (rec_cols_of(g.reach)), so the reference's own default (h = 4 lattice
+// spacings, cell = h/4, reach 4: 81 columns of <= 12 candidates) replays records like the dam break
+// (h = 2 spacings, reach 2: 25 columns).
+constexpr int REC_REACH_MAX = 4;                                       // reach the records support
+__host__ __device__ constexpr uint32_t rec_cols_of(int reach) { return (uint32_t)((2 * reach + 1) * (2 * reach + 1)); }
 // Behind the records and the control words: the queue of deferred slots (sph_passes.cu "deferred
 // singles"): two counters (density pass, force pass), then up to n slot numbers.
-__host__ __device__ constexpr size_t rec_queue_offset(size_t n) { return ((4 * (size_t)REC_COLS + 1) * ((n + 1) / 2) + 3) & ~(size_t)3; }
+__host__ __device__ constexpr size_t rec_queue_offset(size_t n, uint32_t cols) { return ((4 * (size_t)cols + 1) * ((n + 1) / 2) + 3) & ~(size_t)3; }
 // words of the record buffer for a capacity of n slots
-constexpr size_t rec_buffer_words(size_t n) { return rec_queue_offset(n) + 4 + n; }
+constexpr size_t rec_buffer_words(size_t n, uint32_t cols) { return rec_queue_offset(n, cols) + 4 + n; }
 
 // Uniform-grid definition (DESIGN.md "Grid").  The same arithmetic is restated in
 // oracle/sph_oracle.c:oracle_grid_setup / cell_key so keys can be compared bit-exactly.

@@ -40,7 +40,8 @@ struct nprsph_ctx {
     uint32_t* counts_rho = nullptr;
     uint32_t* counts_force = nullptr;
     void* sort_ws = nullptr;
-    uint32_t* hitmask = nullptr;        // column records, rho -> force (sph_passes.cu); rec_buffer_words(cap)
+    uint32_t* hitmask = nullptr;        // column records, rho -> force (sph_passes.cu)
+    size_t hitmask_words = 0;           // allocated: rec_buffer_words(record capacity, rec_cols_of(reach))
     bool mask_valid = false;
 
     uint32_t* cell_start = nullptr;
@@ -60,6 +61,18 @@ struct nprsph_ctx {
     uint64_t steps_done = 0;
 
     cudaGraphicsResource* gl_res = nullptr;
+    bool gl_seeded = false;             // the registered GL buffer holds every lane of the records
+
+    // streaming interface (nprsph_upload_state / nprsph_download_positions): two copy streams so
+    // that a step's result leaves while the next step's inputs arrive and the step itself runs
+    static constexpr int STAGE_CHUNKS = 4;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_chunk[STAGE_CHUNKS] = {}, ev_imported[2] = {}, ev_published = nullptr, ev_copied = nullptr;
+    float4* stage_in[2] = {nullptr, nullptr};   // [pos | vel] of one upload each, double-buffered
+    float4* stage_pos = nullptr;                // positions in original order for the D2H copy
+    uint64_t stage_cap = 0;
+    int stage_cur = 0;
+    bool d2h_pending = false;
 
     nprsph::DistState* dist = nullptr;   // non-null once nprsph_dist_init() succeeded
 };
@@ -93,6 +106,10 @@ int fail(nprsph_ctx* c, int code, const char* fmt, const char* detail = "");
 
 // api.cu
 int refresh_params(nprsph_ctx* c);
+// (re)allocate the column-record buffer for `slots` slots and walks of `reach` cells; frees it when
+// the records cannot describe such walks (the passes then re-test their candidates)
+int ensure_records(nprsph_ctx* c, uint64_t slots, int reach);
+int effective_subdiv(const nprsph_ctx* c);
 template <typename T>
 cudaError_t realloc_dev(T*& p, size_t count) {
     if (p) { cudaError_t e = cudaFree(p); p = nullptr; if (e != cudaSuccess) return e; }

@@ -85,24 +85,6 @@ constexpr int TPB = 256;
 inline unsigned blocks_for(uint64_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 
 // ---- kernels ---------------------------------------------------------------------------------------
-// Sentinel keys of the slab sort.  All high bits set, so a sort on the low b bits keeps them behind
-// every cell key (in this order) as long as the cell keys stay below 2^b - 4: the digit passes
-// only have to cover the OCCUPIED part of the local grid (prepare_group), not the long empty
-// stretch of box the last rank of a dam break owns.
-constexpr uint32_t KEY_NAN = 0xFFFFFFFCu;       // stays on its rank for ever, in no cell
-constexpr uint32_t KEY_GONE_L = 0xFFFFFFFDu;    // belongs to the left rank
-constexpr uint32_t KEY_GONE_R = 0xFFFFFFFEu;    // belongs to the right rank
-
-__device__ __forceinline__ uint32_t cell_key_slab(float x, float y, float z, const GridDev& g, int W, int R) {
-    if (pos_is_nan(x, y, z)) return KEY_NAN;
-    const int cxl = cell_x_unclamped(x, g);
-    if (cxl < R) return KEY_GONE_L;
-    if (cxl >= R + W) return KEY_GONE_R;
-    const int cy = cell_coord(y, g.lo[1], g.inv_cell_d, g.dim[1]);
-    const int cz = cell_coord(z, g.lo[2], g.inv_cell_d, g.dim[2]);
-    return ((uint32_t)cxl * (uint32_t)g.dim[1] + (uint32_t)cy) * (uint32_t)g.dim[2] + (uint32_t)cz;
-}
-
 // candidate particles of the global block scene for this rank: lattice planes [i0, i0+ni)
 __device__ __forceinline__ uint32_t hash32(uint32_t seed, uint32_t idx) {
     uint32_t x = seed ^ (idx * 0x9E3779B9u);
@@ -136,63 +118,18 @@ k_slab_scene(float4* __restrict__ posid, float4* __restrict__ velrho, uint32_t* 
     keys[t] = cell_key_slab(c[0], c[1], c[2], g, W, R);
 }
 
-// One own particle's new key -> leaver into the migration buffer, boundary-layer / NaN counts.
-// Every lane of the warp calls it (key 0xFFFFFFFF for lanes without a particle).
-// send == nullptr: leavers are only counted (scene distribution).
-__device__ __forceinline__ void classify_key(uint32_t key, const float4& p, const float4& v, const GridDev& g,
-                                             int W, int R, Migrant* __restrict__ sendL,
-                                             Migrant* __restrict__ sendR, uint32_t cap_mig,
-                                             uint32_t* __restrict__ counts) {
-    const uint32_t plane = (uint32_t)g.dim[1] * (uint32_t)g.dim[2];
-    const bool goneL = key == KEY_GONE_L, goneR = key == KEY_GONE_R;
-    const bool isnan = key == KEY_NAN;
-    const bool valid = key < KEY_NAN;
-    const uint32_t cxl = valid ? key / plane : 0u;
-    const bool inL = valid && cxl < (uint32_t)(2 * R);
-    const bool inR = valid && cxl >= (uint32_t)W;
-    if (goneL || goneR) {
-        const uint32_t slot = atomicAdd(counts + (goneL ? CNT_LEAVE_L : CNT_LEAVE_R), 1u);
-        Migrant* dst = goneL ? sendL : sendR;
-        if (dst) {
-            if (slot < cap_mig) { dst[slot].posid = p; dst[slot].velrho = v; }
-            else counts[CNT_ERR_OVERFLOW] = 1u;
-        }
-    }
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t mL = __ballot_sync(0xffffffffu, inL), mR = __ballot_sync(0xffffffffu, inR);
-    const uint32_t mN = __ballot_sync(0xffffffffu, isnan);
-    if (lane == 0) {
-        if (mL) atomicAdd(counts + CNT_HALO_L, (uint32_t)__popc(mL));
-        if (mR) atomicAdd(counts + CNT_HALO_R, (uint32_t)__popc(mR));
-        if (mN) atomicAdd(counts + CNT_NAN, (uint32_t)__popc(mN));
-    }
-    // highest occupied x layer: the cell table and the sort only have to reach `reach` layers
-    // beyond it (the last rank of a dam break owns a long empty stretch of the box).  Reduced per
-    // block and checked against the current value first: half a million warps hammering one L2
-    // address -- with an atomic or with a load -- cost more than the rest of the kernel.
-    __shared__ uint32_t s_xmax;
-    if (threadIdx.x == 0) s_xmax = 0u;
-    __syncthreads();
-    const uint32_t xm = __reduce_max_sync(0xffffffffu, cxl);
-    if (lane == 0 && xm) atomicMax(&s_xmax, xm);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_xmax > __ldcg(counts + CNT_XMAX)) atomicMax(counts + CNT_XMAX, s_xmax);
-}
-
 // stand-alone classification of unsorted own keys (after a scene / upload; a step classifies
 // inside k_integrate_slab)
 __global__ void __launch_bounds__(TPB)
 k_classify(const uint32_t* __restrict__ keys, const float4* __restrict__ posid,
-           const float4* __restrict__ velrho, uint32_t n, GridDev g, int W, int R,
-           Migrant* __restrict__ sendL, Migrant* __restrict__ sendR, uint32_t cap_mig,
-           uint32_t* __restrict__ counts) {
+           const float4* __restrict__ velrho, uint32_t n, const __grid_constant__ SlabNext sn) {
     const uint32_t s = blockIdx.x * TPB + threadIdx.x;
     const bool live = s < n;
-    const uint32_t key = live ? keys[s] : 0xFFFFFFFFu;         // (out of range: none of the classes)
+    const uint32_t key = live ? keys[s] : KEY_NONE;            // (out of range: none of the classes)
     const bool gone = key == KEY_GONE_L || key == KEY_GONE_R;
-    const float4 p = (gone && sendL) ? posid[s] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 v = (gone && sendL) ? velrho[s] : make_float4(0.f, 0.f, 0.f, 0.f);
-    classify_key(key, p, v, g, W, R, sendL, sendR, cap_mig, counts);
+    const float4 p = (gone && sn.sendL) ? posid[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = (gone && sn.sendL) ? velrho[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+    classify_key(key, p, v, sn);
 }
 
 __global__ void __launch_bounds__(TPB)
@@ -204,17 +141,24 @@ k_migrant_ids(const Migrant* __restrict__ recv, uint32_t n, uint32_t* __restrict
 // immigrants, in ascending particle-id order, behind the own particles; their keys
 __global__ void __launch_bounds__(TPB)
 k_unpack_migrants(const Migrant* __restrict__ recv, const uint32_t* __restrict__ order, uint32_t n,
-                  float4* __restrict__ posid, float4* __restrict__ velrho,
-                  uint32_t* __restrict__ keys, GridDev g, int W, int R, uint32_t* __restrict__ counts) {
+                  uint32_t n_from_left, float4* __restrict__ posid, float4* __restrict__ velrho,
+                  uint32_t* __restrict__ keys, GridDev g, int W, int R, uint32_t* __restrict__ errs) {
     const uint32_t t = blockIdx.x * TPB + threadIdx.x;
     if (t >= n) return;
-    const Migrant m = recv[order ? order[t] : t];
+    const uint32_t src = order ? order[t] : t;
+    const Migrant m = recv[src];
     posid[t] = m.posid;
     velrho[t] = m.velrho;
     const uint32_t key = cell_key_slab(m.posid.x, m.posid.y, m.posid.z, g, W, R);
     keys[t] = key;
-    // an immigrant must land in the boundary layer next to the rank it came from
-    if (key >= KEY_NAN) counts[CNT_ERR_IMMIGRANT] = 1u;
+    // An immigrant must land in the boundary layer next to the rank it came from: the host sized
+    // this step's halo messages and ghost ranges on that assumption (hL/hR in prepare_group).  A
+    // particle that crossed more than `reach` cell layers in one step (|v_x| dt > reach * cell)
+    // breaks it; the flag is sticky and fails the next collective call.
+    const uint32_t cxl = key < KEY_NAN ? key / ((uint32_t)g.dim[1] * (uint32_t)g.dim[2]) : 0xFFFFFFFFu;
+    const bool ok = src < n_from_left ? (cxl >= (uint32_t)R && cxl < (uint32_t)(2 * R))
+                                      : (cxl >= (uint32_t)W && cxl < (uint32_t)(W + R));
+    if (!ok) errs[ERR_IMMIGRANT] = 1u;
 }
 
 // ---- cell table of a slab ---------------------------------------------------------------------------
@@ -240,10 +184,13 @@ __device__ __forceinline__ void fill_cells(uint32_t lo, uint32_t hi, uint32_t sl
 // n: own particles after migration; n_valid of them (the first) have cells, the rest are NaN.
 // Cells [cell_lo, cell_hi] belong to the region; cells above the last own key hold tail_slot (the
 // first ghost-R slot: the NaN block in between is harmless, a NaN candidate is never a hit).
+// frc_in != nullptr (the prepare after an upload / scene): the force array follows the permutation
+// too, into frc_out; sources >= n_frc (immigrants, which travel without their force) get zero.
 __global__ void __launch_bounds__(TPB)
 k_gather_cells_slab(const uint32_t* __restrict__ sorted_keys, const uint32_t* __restrict__ perm,
                     const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
-                    float4* __restrict__ pos_out, float4* __restrict__ vel_out, uint32_t n,
+                    float4* __restrict__ pos_out, float4* __restrict__ vel_out,
+                    const float4* __restrict__ frc_in, float4* __restrict__ frc_out, uint32_t n_frc, uint32_t n,
                     uint32_t n_valid, uint32_t slot_base, uint32_t tail_slot, uint32_t cell_lo,
                     uint32_t cell_hi, uint32_t* __restrict__ table, uint4* __restrict__ gap_list,
                     uint32_t* __restrict__ gap_count) {
@@ -252,6 +199,7 @@ k_gather_cells_slab(const uint32_t* __restrict__ sorted_keys, const uint32_t* __
         const uint32_t src = perm[s];
         pos_out[s] = pos_in[src];
         vel_out[s] = vel_in[src];
+        if (frc_in) frc_out[s] = src < n_frc ? frc_in[src] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (s > n_valid) return;
     const uint32_t lo = (s == 0) ? cell_lo : max(sorted_keys[s - 1] + 1u, cell_lo);
@@ -278,11 +226,9 @@ k_ghost_cells(const float4* __restrict__ posid, uint32_t n, uint32_t slot_base, 
 __global__ void __launch_bounds__(TPB)
 k_integrate_slab(float4* __restrict__ posid, float4* __restrict__ velrho,
                  const float4* __restrict__ forcep, uint32_t* __restrict__ keys, uint32_t n,
-                 GridDev g, SphDev sp, int W, int R, const __grid_constant__ ColliderSet cs,
-                 Migrant* __restrict__ sendL, Migrant* __restrict__ sendR, uint32_t cap_mig,
-                 uint32_t* __restrict__ counts) {
+                 SphDev sp, const __grid_constant__ ColliderSet cs, const __grid_constant__ SlabNext sn) {
     const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-    uint32_t key = 0xFFFFFFFFu;
+    uint32_t key = KEY_NONE;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p;
     if (i < n) {
         p = posid[i];
@@ -291,12 +237,16 @@ k_integrate_slab(float4* __restrict__ posid, float4* __restrict__ velrho,
         integrate_particle(p, v, f, sp, cs);
         posid[i] = p;
         velrho[i] = v;
-        key = cell_key_slab(p.x, p.y, p.z, g, W, R);
+        key = cell_key_slab(p.x, p.y, p.z, sn.g, sn.W, sn.R);
         keys[i] = key;
     }
     // the next step's classification (leavers, boundary layers, NaN, top layer) while the particle
     // is in registers
-    classify_key(key, p, v, g, W, R, sendL, sendR, cap_mig, counts);
+    classify_key(key, p, v, sn);
+}
+
+__global__ void k_set_words(uint32_t* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
 }
 
 __global__ void __launch_bounds__(TPB)
@@ -377,31 +327,70 @@ int exchange_group(nprsph_ctx** cs, int n, const Xfer* x, bool on_comm = false) 
 }
 
 // ---- host-side phases -------------------------------------------------------------------------------
+// local grid of the slab [X0, X0 + W): own layers plus R ghost layers on each side, addressed with
+// global cell arithmetic minus the integer offset x_off
+GridDev local_grid_of(const nprsph_ctx* c, int X0, int W, int R) {
+    GridDev g = c->grid;
+    g.x_off = X0 - R;
+    g.dimx_global = c->grid.dim[0];
+    g.dim[0] = W + 2 * R;
+    g.num_cells = (uint32_t)((uint64_t)g.dim[0] * g.dim[1] * g.dim[2]);
+    return g;
+}
+
 int setup_local_grid(nprsph_ctx* c) {
     DistState* d = c->dist;
     int rc = refresh_params(c);
     if (rc) return rc;
     d->R = c->grid.reach;
-    d->lg = c->grid;
-    d->lg.x_off = d->X0 - d->R;
-    d->lg.dimx_global = c->grid.dim[0];
-    d->lg.dim[0] = d->W + 2 * d->R;
-    const uint64_t cells = (uint64_t)d->lg.dim[0] * d->lg.dim[1] * d->lg.dim[2];
+    d->W = d->X1 - d->X0;
+    const uint64_t cells = (uint64_t)(d->W + 2 * d->R) * c->grid.dim[1] * c->grid.dim[2];
     if (cells + 4 >= (1ull << 32)) return fail(c, NPRSPH_ERR_INVALID, "local grid too large%s");
-    d->lg.num_cells = (uint32_t)cells;
+    d->lg = local_grid_of(c, d->X0, d->W, d->R);
     int bits = 1;
     while (bits < 32 && (1ull << bits) < cells + 4) bits++;      // cell keys below 2^bits - 4 (sentinels)
     d->key_bits = bits;
     const size_t need = (size_t)cells + 4;
     if (need > c->cell_cap) {
-        CK(c, realloc_dev(c->cell_start, need));
-        c->cell_cap = need;
+        // (re-balancing widens a slab one layer at a time: leave room for a quarter more layers)
+        const size_t slack = d->rebalance_every ? (size_t)(d->W / 4 + 2) * c->grid.dim[1] * c->grid.dim[2] : 0;
+        size_t want = need + slack;
+        if (want + 4 >= ((size_t)1 << 32)) want = need;
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, realloc_dev(c->cell_start, want));
+        c->cell_cap = want;
+        CK(c, cudaMemsetAsync(c->cell_start, 0, want * sizeof(uint32_t), c->stream));
     }
     const size_t gaps = gap_list_capacity((uint32_t)cells + 2u, d->cap_total ? d->cap_total : 1);
     if (gaps > c->gap_cap) {
-        CK(c, realloc_dev(c->gap_list, gaps));
-        c->gap_cap = gaps;
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, realloc_dev(c->gap_list, gaps + gaps / 4));
+        c->gap_cap = gaps + gaps / 4;
     }
+    return NPRSPH_OK;
+}
+
+// what the key-producing kernels of this step need (slab.cuh): the faces the NEXT prepare will use
+SlabNext slab_next(const nprsph_ctx* c, bool with_send) {
+    const DistState* d = c->dist;
+    SlabNext sn;
+    sn.W = d->X1_next - d->X0_next;
+    sn.R = d->R;
+    sn.g = local_grid_of(c, d->X0_next, sn.W, d->R);
+    sn.sendL = with_send ? d->sendL : nullptr;
+    sn.sendR = with_send ? d->sendR : nullptr;
+    sn.cap_mig = d->cap_mig;
+    sn.counts = d->d_counts;
+    sn.errs = d->d_counts + 3 * CNT_WORDS;
+    return sn;
+}
+
+// zero this step's counters and publish the host-known ones the neighbours need for re-balancing
+int reset_counts(nprsph_ctx* c) {
+    DistState* d = c->dist;
+    CK(c, cudaMemsetAsync(d->d_counts, 0, 3 * CNT_WORDS * sizeof(uint32_t), c->stream));
+    k_set_words<<<1, 1, 0, c->stream>>>(d->d_counts + CNT_NOWN, d->n_own, d->cap_own - d->n_own,
+                                         (uint32_t)(d->X1_next - d->X0_next), d->cap_mig);
     return NPRSPH_OK;
 }
 
@@ -421,8 +410,7 @@ int alloc_slab(nprsph_ctx* c, uint64_t cap_own, uint64_t cap_ghost, uint64_t cap
     CK(c, realloc_dev(c->frc[0], total));
     CK(c, realloc_dev(c->frc[1], (size_t)0));
     { char* w = (char*)c->sort_ws; CK(c, realloc_dev(w, sort_workspace_bytes(total))); c->sort_ws = w; }
-    // (column descriptors hold 27-bit slots: beyond that the force pass re-tests its candidates)
-    CK(c, realloc_dev(c->hitmask, (c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) || total > (1u << 27) ? (size_t)0 : rec_buffer_words(total)));
+    { int rc = ensure_records(c, total, c->grid.reach); if (rc) return rc; }
     if (c->cfg.flags & NPRSPH_FLAG_COUNT_NEIGHBOURS) {
         CK(c, realloc_dev(c->counts_rho, total));
         CK(c, realloc_dev(c->counts_force, total));
@@ -461,22 +449,54 @@ struct PhaseTrace {
 };
 static PhaseTrace g_trace;
 
+// Re-balancing: every `rebalance_every` steps each interior slab face may move by
+// ONE x layer towards the lighter rank.  Both ranks of a face evaluate this function on the same
+// numbers (their two counter blocks, exchanged in phase (1)), so they take the same decision
+// without talking to anyone else; the layer that changes hands simply becomes "gone" under the
+// next local grid and travels through the ordinary migration path of the next prepare.
+// a = counters of the left rank of the face, b = of the right rank.  Returns -1 (face moves left:
+// a gives its last layer to b), +1 (b gives its first layer to a) or 0.
+int face_move(const uint32_t* a, const uint32_t* b, int R, uint32_t cap_ghost) {
+    const int64_t nA = a[CNT_NOWN], nB = b[CNT_NOWN];
+    const int64_t layerA = (a[CNT_HALO_R] + R - 1) / R, layerB = (b[CNT_HALO_L] + R - 1) / R;   // particles per x layer at the face
+    const int64_t cap_mig = a[CNT_CAPMIG] < b[CNT_CAPMIG] ? a[CNT_CAPMIG] : b[CNT_CAPMIG];
+    const int wmin = 2 * R + 2;           // a slab keeps 2R layers after giving one away on EACH face
+    auto fits = [&](int64_t layer, int64_t free_rx) {
+        // the hand-over rides on top of the ordinary migrants and becomes ghosts of the giver
+        return 2 * layer + 1024 <= cap_mig && 2 * layer + 65536 <= free_rx &&
+               (int64_t)(R + 2) * layer * 3 / 2 <= (int64_t)cap_ghost;
+    };
+    if (nA > nB + 2 * layerA && (int)a[CNT_WIDTH] >= wmin && fits(layerA, b[CNT_FREE])) return -1;
+    if (nB > nA + 2 * layerB && (int)b[CNT_WIDTH] >= wmin && fits(layerB, a[CNT_FREE])) return +1;
+    return 0;
+}
+
 // Everything between "positions + unsorted slab keys of the own particles are final" and "cell
 // table and ghosts are ready for k_rho", for all local ranks in lock step.
 int prepare_group(nprsph_ctx** cs, int n) {
     Xfer x[64] = {};
     g_trace.begin(cs, n);
+    // (0) the faces decided one step ago take effect: the keys at hand were computed against them
+    for (int r = 0; r < n; r++) {
+        nprsph_ctx* c = cs[r]; DistState* d = c->dist;
+        CK(c, cudaSetDevice(c->cfg.device));
+        if (d->X0_next != d->X0 || d->X1_next != d->X1) {
+            d->X0 = d->X0_next; d->X1 = d->X1_next;
+            int rc = setup_local_grid(c);
+            if (rc) return rc;
+        }
+    }
     // (1) classify + counter exchange, one host sync
     for (int r = 0; r < n; r++) {
         nprsph_ctx* c = cs[r]; DistState* d = c->dist;
         CK(c, cudaSetDevice(c->cfg.device));
         if (!d->classified) {
-            CK(c, cudaMemsetAsync(d->d_counts, 0, 3 * CNT_WORDS * sizeof(uint32_t), c->stream));
+            int rc = reset_counts(c);
+            if (rc) return rc;
             if (d->n_own)
                 k_classify<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
-                c->keys[0], c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, d->n_own, d->lg,
-                d->W, d->R, d->first_prepare ? nullptr : d->sendL, d->first_prepare ? nullptr : d->sendR,
-                d->cap_mig, d->d_counts);
+                    c->keys[0], c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, d->n_own,
+                    slab_next(c, !d->first_prepare));
         }
         d->classified = false;
         x[r] = {d->d_counts, CNT_WORDS * 4, d->d_counts, CNT_WORDS * 4,
@@ -486,7 +506,7 @@ int prepare_group(nprsph_ctx** cs, int n) {
     if (rc) return rc;
     for (int r = 0; r < n; r++) {
         nprsph_ctx* c = cs[r];
-        CK(c, cudaMemcpyAsync(c->dist->h_counts, c->dist->d_counts, 3 * CNT_WORDS * sizeof(uint32_t),
+        CK(c, cudaMemcpyAsync(c->dist->h_counts, c->dist->d_counts, (3 * CNT_WORDS + ERR_WORDS) * sizeof(uint32_t),
                               cudaMemcpyDeviceToHost, c->stream));
     }
     for (int r = 0; r < n; r++) CK(cs[r], cudaStreamSynchronize(cs[r]->stream));
@@ -499,8 +519,12 @@ int prepare_group(nprsph_ctx** cs, int n) {
         const uint32_t* mine = d->h_counts;
         const uint32_t* fromL = d->h_counts + CNT_WORDS;
         const uint32_t* fromR = d->h_counts + 2 * CNT_WORDS;
+        const uint32_t* errs = d->h_counts + 3 * CNT_WORDS;
         const bool hasL = d->rank > 0, hasR = d->rank + 1 < d->world;
-        if (mine[CNT_ERR_OVERFLOW]) return fail(c, NPRSPH_ERR_NOMEM, "migration buffer overflow (raise max_migrate)%s");
+        if (errs[ERR_OVERFLOW]) return fail(c, NPRSPH_ERR_NOMEM, "migration buffer overflow (raise max_migrate)%s");
+        if (errs[ERR_IMMIGRANT])
+            return fail(c, NPRSPH_ERR_STATE, "a particle crossed more than `reach` cell layers of a slab face in one step "
+                        "(|v_x| dt > reach * cell): halo sizes of the last step were wrong%s");
         dropped[r] = mine[CNT_LEAVE_L] + mine[CNT_LEAVE_R];
         const bool fp = d->first_prepare;
         leaveL[r] = fp ? 0u : mine[CNT_LEAVE_L];
@@ -526,6 +550,15 @@ int prepare_group(nprsph_ctx** cs, int n) {
         if (d->gL > d->cap_ghost || d->gR > d->cap_ghost)
             return fail(c, NPRSPH_ERR_NOMEM, "ghost capacity exceeded (raise max_ghost)%s");
         d->migrated_total += leaveL[r] + leaveR[r];
+        d->last_migrated = leaveL[r] + leaveR[r];
+        // faces of the prepare after this one (the coming step keys its particles against them)
+        if (d->rebalance_every > 0 && !fp && d->steps_done > 0 && d->steps_done % (uint64_t)d->rebalance_every == 0) {
+            const int mL = hasL ? face_move(fromL, mine, d->R, d->cap_ghost) : 0;
+            const int mR = hasR ? face_move(mine, fromR, d->R, d->cap_ghost) : 0;
+            d->X0_next = d->X0 + mL;
+            d->X1_next = d->X1 + mR;
+            d->rebalanced += (uint64_t)((mL != 0) + (mR != 0));
+        }
         x[r] = {d->sendL, leaveL[r] * sizeof(Migrant), d->sendR, leaveR[r] * sizeof(Migrant),
                 d->recv, inL[r] * sizeof(Migrant), d->recv + inL[r], inR[r] * sizeof(Migrant)};
     }
@@ -552,8 +585,8 @@ int prepare_group(nprsph_ctx** cs, int n) {
                 order = in_b ? ids + 6 * d->cap_mig : ids + 2 * d->cap_mig;
             }
             k_unpack_migrants<<<blocks_for(n_in), TPB, 0, c->stream>>>(
-                d->recv, order, n_in, pos + d->n_own, vel + d->n_own, c->keys[0] + d->n_own, d->lg, d->W,
-                d->R, d->d_counts);
+                d->recv, order, n_in, inL[r], pos + d->n_own, vel + d->n_own, c->keys[0] + d->n_own, d->lg, d->W,
+                d->R, d->d_counts + 3 * CNT_WORDS);
         }
         const uint32_t n_new = n_pre - (d->first_prepare ? dropped[r] : leaveL[r] + leaveR[r]);
         bool in_b = false;
@@ -571,10 +604,19 @@ int prepare_group(nprsph_ctx** cs, int n) {
             const uint32_t table_len = (d->x_top + 1u) * plane + 4u;
             const uint32_t own_hi = ((d->rank + 1 < d->world) ? (uint32_t)(d->R + d->W) * plane : table_len) - 1u;
             CK(c, cudaMemsetAsync(c->gap_count, 0, 2 * sizeof(uint32_t), c->stream));
+            // after an upload / scene the force array follows the permutation too (through the idle
+            // AoS staging buffer): later steps recompute it before anyone can read it
+            float4* frc_tmp = d->gather_force ? (float4*)c->aos : nullptr;
             k_gather_cells_slab<<<blocks_for((uint64_t)n_new + 1), TPB, 0, c->stream>>>(
                 in_b ? c->keys[1] : c->keys[0], in_b ? c->vals[1] : c->vals[0], pos, vel,
-                c->pos[nxt] + d->own_off, c->vel[nxt] + d->own_off, n_new, n_new - d->n_nan, d->own_off,
+                c->pos[nxt] + d->own_off, c->vel[nxt] + d->own_off,
+                frc_tmp ? c->frc[0] + d->own_off : nullptr, frc_tmp, d->n_own, n_new,
+                n_new - d->n_nan, d->own_off,
                 d->own_off + n_new, (uint32_t)d->R * plane, own_hi, c->cell_start, c->gap_list, c->gap_count);
+            if (frc_tmp && n_new)
+                CK(c, cudaMemcpyAsync(c->frc[0] + d->own_off, frc_tmp, (size_t)n_new * sizeof(float4),
+                                      cudaMemcpyDeviceToDevice, c->stream));
+            d->gather_force = false;
         }
         c->cur = nxt;
         d->n_own = n_new;
@@ -649,7 +691,7 @@ int step_group(nprsph_ctx** cs, int n, cudaEvent_t* ev = nullptr) {
     // (velocity, rho) of the boundary layers travels on the communication streams while the
     // compute stream runs the force pass for the interior slots, whose walks touch no ghost cell;
     // the two boundary layers (and the NaN block) follow once the ghosts' (v, rho) have landed.
-    // Range edges are even slots so that the slot pairs of k_rho / k_force_mask stay aligned.
+    // Range edges are even slots so that the slot pairs of k_rho / k_force_records stay aligned.
     for (int r = 0; r < n; r++) CK(cs[r], cudaEventRecord(cs[r]->dist->ev_rho, cs[r]->stream));
     for (int r = 0; r < n; r++)                    // LOCAL: ranks share one compute stream, so the
         CK(cs[r], cudaStreamWaitEvent(cs[r]->dist->comm_stream, cs[n - 1]->dist->ev_rho, 0));   // last event covers all
@@ -667,20 +709,37 @@ int step_group(nprsph_ctx** cs, int n, cudaEvent_t* ev = nullptr) {
         if (in0 > own_end) in0 = own_end;
         if (in1 < in0) in1 = in0;
         const float4* P = c->pos[c->cur]; const float4* V = c->vel[c->cur];
-        launch_force(P, V, c->frc[0], c->cell_start, in0, in1 - in0, d->lg, c->sph, nullptr, c->hitmask,
-                     d->cap_total, c->stream);
+        // Passes 2 + 3 as one launch per slot range when the density pass left its column records
+        // (the single-GPU step's fused kernel, plus slab keys and the next step's classification in
+        // its epilogue); otherwise force launches followed by k_integrate_slab.
+        const bool fused = !(c->cfg.flags & NPRSPH_FLAG_NO_FUSE) && c->hitmask && records_fit(d->lg.reach, d->cap_total);
+        const int nxt = 1 - c->cur;
+        const SlabNext sn = slab_next(c, true);
+        if (fused) { rc = reset_counts(c); if (rc) return rc; }
+        auto force_range = [&](uint32_t first, uint32_t count) {
+            if (fused)
+                launch_force_integrate_slab(P, V, c->frc[0], c->cell_start, first, count, d->lg, c->sph, c->hitmask,
+                                            d->cap_total, c->pos[nxt], c->vel[nxt], c->keys[0], d->own_off,
+                                            c->colliders, sn, c->stream);
+            else
+                launch_force(P, V, c->frc[0], c->cell_start, first, count, d->lg, c->sph, nullptr, c->hitmask,
+                             d->cap_total, c->stream);
+        };
+        force_range(in0, in1 - in0);
         for (int q = 0; q < n; q++) CK(c, cudaStreamWaitEvent(c->stream, cs[q]->dist->ev_halo, 0));
-        launch_force(P, V, c->frc[0], c->cell_start, d->own_off, in0 - d->own_off, d->lg, c->sph, nullptr,
-                     c->hitmask, d->cap_total, c->stream);
-        launch_force(P, V, c->frc[0], c->cell_start, in1, own_end - in1, d->lg, c->sph, nullptr,
-                     c->hitmask, d->cap_total, c->stream);
+        force_range(d->own_off, in0 - d->own_off);
+        force_range(in1, own_end - in1);
         if (ev && r == 0) CK(c, cudaEventRecord(ev[4], c->stream));
-        CK(c, cudaMemsetAsync(d->d_counts, 0, 3 * CNT_WORDS * sizeof(uint32_t), c->stream));
-        if (d->n_own)
-            k_integrate_slab<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
-                c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off,
-                c->keys[0], d->n_own, d->lg, c->sph, d->W, d->R, c->colliders, d->sendL, d->sendR,
-                d->cap_mig, d->d_counts);
+        if (fused) {
+            c->cur = nxt;
+        } else {
+            rc = reset_counts(c);
+            if (rc) return rc;
+            if (d->n_own)
+                k_integrate_slab<<<blocks_for(d->n_own), TPB, 0, c->stream>>>(
+                    c->pos[c->cur] + d->own_off, c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off,
+                    c->keys[0], d->n_own, c->sph, c->colliders, sn);
+        }
         d->classified = true;                       // counts and migration buffers are ready
         CK(c, cudaGetLastError());
         d->prepared = false;                        // positions moved: keys/ghosts/table are stale
@@ -746,6 +805,14 @@ int nprsph_slab_partition(const uint64_t* hist, int dimx, int world, int min_wid
     return NPRSPH_OK;
 }
 
+static_assert(NPRSPH_SLAB_COUNTER_WORDS == CNT_WORDS && NPRSPH_CNT_OWN == CNT_NOWN && NPRSPH_CNT_FREE == CNT_FREE &&
+              NPRSPH_CNT_WIDTH == CNT_WIDTH && NPRSPH_CNT_CAP_MIGRATE == CNT_CAPMIG && NPRSPH_CNT_HALO_R == CNT_HALO_R,
+              "public counter layout");
+int nprsph_slab_face_move(const uint32_t* a, const uint32_t* b, int reach, uint32_t cap_ghost) {
+    if (!a || !b || reach < 1) return 0;
+    return face_move(a, b, reach, cap_ghost);
+}
+
 int nprsph_dist_unique_id(uint8_t id[128]) {
     if (!id) return NPRSPH_ERR_INVALID;
     NcclApi* api = nccl();
@@ -767,8 +834,11 @@ int nprsph_dist_init(nprsph_ctx* c, const nprsph_dist_config* cfg) {
     if (!d) return fail(c, NPRSPH_ERR_NOMEM, "out of host memory%s");
     d->rank = cfg->rank; d->world = cfg->world; d->transport = cfg->transport;
     c->dist = d;
-    CK(c, cudaMalloc(&d->d_counts, 3 * CNT_WORDS * sizeof(uint32_t)));
-    CK(c, cudaMallocHost(&d->h_counts, 3 * CNT_WORDS * sizeof(uint32_t)));
+    CK(c, cudaMalloc(&d->d_counts, (3 * CNT_WORDS + ERR_WORDS) * sizeof(uint32_t)));
+    CK(c, cudaMemset(d->d_counts, 0, (3 * CNT_WORDS + ERR_WORDS) * sizeof(uint32_t)));
+    CK(c, cudaMallocHost(&d->h_counts, (3 * CNT_WORDS + ERR_WORDS) * sizeof(uint32_t)));
+    // (a decision sees the neighbours' counts of the step before: at least every second step)
+    d->rebalance_every = cfg->rebalance_every > 0 ? (cfg->rebalance_every < 2 ? 2 : cfg->rebalance_every) : 0;
     CK(c, cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
     CK(c, cudaEventCreateWithFlags(&d->ev_rho, cudaEventDisableTiming));
     CK(c, cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming));
@@ -817,6 +887,7 @@ int nprsph_dist_scene_block(nprsph_ctx* c, int nx, int ny, int nz, float spacing
     rc = nprsph_slab_partition(hist, g.dim[0], d->world, 2 * R, bounds);
     if (rc) { delete[] hist; delete[] bounds; return fail(c, NPRSPH_ERR_INVALID, "grid too narrow for this many ranks (each slab needs 2*reach cells)%s"); }
     d->X0 = bounds[d->rank]; d->X1 = bounds[d->rank + 1]; d->W = d->X1 - d->X0;
+    d->X0_next = d->X0; d->X1_next = d->X1;
     // candidate lattice planes: those whose cell (ignoring jitter) is within one cell of the slab
     int i0 = nx, i1 = 0;
     for (int i = 0; i < nx; i++) {
@@ -849,11 +920,14 @@ int nprsph_dist_scene_block(nprsph_ctx* c, int nx, int ny, int nz, float spacing
     CK(c, cudaGetLastError());
     d->n_own = (uint32_t)n_cand;
     d->first_prepare = true;
+    d->gather_force = false;         // (the scene's force array is zero)
     d->prepared = false;
     d->classified = false;
     d->ready = true;
     d->steps_done = 0;
     d->migrated_total = 0;
+    d->rebalanced = 0;
+    CK(c, cudaMemsetAsync(c->frc[0], 0, (size_t)d->cap_total * sizeof(float4), c->stream));
     return NPRSPH_OK;
 }
 
@@ -899,9 +973,16 @@ int nprsph_dist_download(nprsph_ctx** ranks, int n_local, int which, nprsph_part
     int rc = check_group(ranks, n_local);
     if (rc) return rc;
     if (which < 0 || which >= n_local || !n_out) return NPRSPH_ERR_INVALID;
-    // ownership must be current (migration of the last integrate applied): collective prepare
-    rc = ensure_prepared(ranks, n_local);
-    if (rc) return rc;
+    // After a step every particle is still held by exactly one rank (a leaver sits in its old
+    // rank's slots until the next prepare hands it over), and position, velocity, force and density
+    // share one slot order: the records are packed as they are.  Only a freshly distributed scene
+    // still holds candidates of other slabs and needs the (collective) prepare first.
+    bool fresh = false;
+    for (int r = 0; r < n_local; r++) fresh = fresh || ranks[r]->dist->first_prepare;
+    if (fresh) {
+        rc = ensure_prepared(ranks, n_local);
+        if (rc) return rc;
+    }
     nprsph_ctx* c = ranks[which]; DistState* d = c->dist;
     CK(c, cudaSetDevice(c->cfg.device));
     *n_out = d->n_own;
@@ -924,17 +1005,19 @@ int nprsph_dist_upload(nprsph_ctx* c, const nprsph_particle* records, const uint
     DistState* d = c->dist;
     if (!d || !d->ready) return fail(c, NPRSPH_ERR_STATE, "distribute a scene first (slab geometry and capacities)%s");
     if (n > d->cap_own || (n && (!records || !ids))) return fail(c, NPRSPH_ERR_INVALID, "bad upload%s");
+    const SlabNext sn = slab_next(c, false);
     if (n) {
         uint32_t* d_ids = c->vals[1];
         CK(c, cudaMemcpyAsync(c->aos, records, n * 64, cudaMemcpyHostToDevice, c->stream));
         CK(c, cudaMemcpyAsync(d_ids, ids, n * 4, cudaMemcpyHostToDevice, c->stream));
         k_unpack_records<<<blocks_for(n), TPB, 0, c->stream>>>(
             (const float4*)c->aos, d_ids, (uint32_t)n, c->pos[c->cur] + d->own_off,
-            c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off, c->keys[0], d->lg, d->W, d->R);
+            c->vel[c->cur] + d->own_off, c->frc[0] + d->own_off, c->keys[0], sn.g, sn.W, sn.R);
         CK(c, cudaGetLastError());
     }
     d->n_own = (uint32_t)n;
-    d->first_prepare = true;         // records that belong to another slab are dropped, not sent
+    d->first_prepare = false;        // a record of the slab next door is handed over by the next prepare
+    d->gather_force = true;          // the uploaded force / pressure columns follow the re-sort
     d->prepared = false;
     d->classified = false;
     return NPRSPH_OK;
@@ -979,6 +1062,8 @@ int nprsph_dist_get_info(nprsph_ctx* c, nprsph_dist_info* out) {
     out->migrated_total = d->migrated_total; out->steps_done = d->steps_done;
     out->cap_own = d->cap_own; out->cap_ghost = d->cap_ghost;
     out->nan_particles = d->n_nan;
+    out->rebalanced = d->rebalanced;
+    out->last_migrated = d->last_migrated;
     out->sort_bits = (uint32_t)d->sort_bits;
     out->sort_passes = (uint32_t)sort_num_passes(d->sort_bits);
     return NPRSPH_OK;

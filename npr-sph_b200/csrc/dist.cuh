@@ -2,13 +2,9 @@
 #pragma once
 
 #include "context.cuh"
+#include "slab.cuh"
 
 namespace nprsph {
-
-struct Migrant { float4 posid, velrho; };      // one particle changing rank (32 B)
-
-enum { CNT_LEAVE_L = 0, CNT_LEAVE_R, CNT_HALO_L, CNT_HALO_R, CNT_NAN, CNT_XMAX, CNT_ERR_IMMIGRANT,
-       CNT_ERR_OVERFLOW, CNT_WORDS };
 
 struct DistState {
     int rank = 0, world = 1;
@@ -35,10 +31,18 @@ struct DistState {
     uint32_t x_top = 0;                // highest local x cell layer any walk of this step can touch
     bool first_prepare = true;         // candidates that belong to other ranks are dropped, not sent
     uint64_t migrated_total = 0, steps_done = 0;
+    uint32_t last_migrated = 0;        // particles this rank handed over in the last prepare
 
     Migrant *sendL = nullptr, *sendR = nullptr, *recv = nullptr;
-    uint32_t* d_counts = nullptr;      // [3][CNT_WORDS]: mine, from left, from right
+    uint32_t* d_counts = nullptr;      // [3][CNT_WORDS]: mine, from left, from right; then [ERR_WORDS] sticky
     uint32_t* h_counts = nullptr;      // pinned mirror
+    bool gather_force = false;         // the next prepare also permutes the force array (after an upload /
+                                       // scene: later steps recompute the force before anyone reads it)
+    // slab faces the NEXT prepare will use (re-balancing moves a face by one x layer; the step in
+    // between computes its keys against them)
+    int X0_next = 0, X1_next = 0;
+    int rebalance_every = 0;           // steps between re-balancing decisions (0 = static slabs)
+    uint64_t rebalanced = 0;           // face moves so far (both faces of this rank)
     uint32_t* mig_ids = nullptr;       // [4][2*cap_mig] scratch: ids, iota, sorted ids, order
     void* mig_sort_ws = nullptr;
 };

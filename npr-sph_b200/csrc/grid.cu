@@ -47,6 +47,33 @@ k_publish(const float4* __restrict__ posid, const float4* __restrict__ velrho,
     r[12] = v.w; r[13] = f.w;
 }
 
+// ---- positions only, ORIGINAL order: what the renderer reads (attribute 0 = vec4 at offset 0 of the
+// record, Main.cpp:533-535; toon_vs.glsl:17).  The w lane is the record's own (never written by a pass).
+__global__ void __launch_bounds__(TPB)
+k_publish_positions(const float4* __restrict__ posid, const float* __restrict__ aos,
+                    float4* __restrict__ out, uint32_t n) {
+    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    if (s >= n) return;
+    const float4 p = posid[s];
+    const uint32_t id = __float_as_uint(p.w);
+    out[id] = make_float4(p.x, p.y, p.z, aos[16 * (size_t)id + 3]);
+}
+
+// ---- host state (positions, velocities; original order) -> SoA: the inputs of a step.  Force,
+// density and pressure are outputs of the passes and start from zero.
+__global__ void __launch_bounds__(TPB)
+k_import_state(const float4* __restrict__ pos_in, const float4* __restrict__ vel_in, uint32_t first,
+               uint32_t count, float4* __restrict__ posid, float4* __restrict__ velrho,
+               float4* __restrict__ forcep) {
+    const uint32_t k = blockIdx.x * TPB + threadIdx.x;
+    if (k >= count) return;
+    const uint32_t i = first + k;
+    const float4 p = pos_in[k], v = vel_in[k];
+    posid[i] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
+    velrho[i] = make_float4(v.x, v.y, v.z, 0.0f);
+    forcep[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
 // ---- stand-alone cell keys (only when keys are stale: after upload or a grid change) ---------
 __global__ void __launch_bounds__(TPB)
 k_keys(const float4* __restrict__ posid, uint32_t* __restrict__ keys, uint32_t n, GridDev g) {
@@ -162,6 +189,15 @@ void launch_import(const void* aos, float4* posid, float4* velrho, float4* force
 void launch_publish(const float4* posid, const float4* velrho, const float4* forcep, void* aos,
                     uint32_t n, cudaStream_t st) {
     if (n) k_publish<<<blocks_for(n, TPB), TPB, 0, st>>>(posid, velrho, forcep, (float*)aos, n);
+}
+
+void launch_publish_positions(const float4* posid, const void* aos, float4* out, uint32_t n, cudaStream_t st) {
+    if (n) k_publish_positions<<<blocks_for(n, TPB), TPB, 0, st>>>(posid, (const float*)aos, out, n);
+}
+
+void launch_import_state(const float4* pos_in, const float4* vel_in, uint32_t first, uint32_t count,
+                         float4* posid, float4* velrho, float4* forcep, cudaStream_t st) {
+    if (count) k_import_state<<<blocks_for(count, TPB), TPB, 0, st>>>(pos_in, vel_in, first, count, posid, velrho, forcep);
 }
 
 void launch_keys(const float4* posid, uint32_t* keys, uint32_t n, const GridDev& g, cudaStream_t st) {

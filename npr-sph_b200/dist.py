@@ -21,7 +21,8 @@ TRANSPORT_NCCL, TRANSPORT_LOCAL = 0, 1
 class DistConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("transport", C.c_int32), ("nccl_id", C.c_uint8 * 128), ("max_own", C.c_uint64),
-                ("max_ghost", C.c_uint64), ("max_migrate", C.c_uint64)]
+                ("max_ghost", C.c_uint64), ("max_migrate", C.c_uint64),
+                ("rebalance_every", C.c_int32), ("reserved", C.c_int32)]
 
 
 class DistInfo(C.Structure):
@@ -30,7 +31,8 @@ class DistInfo(C.Structure):
                 ("ghosts_right", C.c_uint64), ("nan_particles", C.c_uint64),
                 ("migrated_total", C.c_uint64), ("steps_done", C.c_uint64),
                 ("cap_own", C.c_uint64), ("cap_ghost", C.c_uint64),
-                ("sort_bits", C.c_uint32), ("sort_passes", C.c_uint32)]
+                ("sort_bits", C.c_uint32), ("sort_passes", C.c_uint32),
+                ("rebalanced", C.c_uint64), ("last_migrated", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 def unique_id() -> bytes:
@@ -51,6 +53,19 @@ def slab_partition(hist, world: int, min_width: int) -> np.ndarray:
     return bounds
 
 
+SLAB_COUNTER_WORDS = 12
+CNT_HALO_L, CNT_HALO_R, CNT_OWN, CNT_FREE, CNT_WIDTH, CNT_CAP_MIGRATE = 2, 3, 6, 7, 8, 9
+
+
+def slab_face_move(a, b, reach: int, cap_ghost: int) -> int:
+    """The re-balancing rule for the face between the ranks whose counter blocks are a (left) and b."""
+    a = np.ascontiguousarray(a, np.uint32)
+    b = np.ascontiguousarray(b, np.uint32)
+    assert len(a) == len(b) == SLAB_COUNTER_WORDS
+    u32p = C.POINTER(C.c_uint32)
+    return int(B.load().nprsph_slab_face_move(a.ctypes.data_as(u32p), b.ctypes.data_as(u32p), reach, cap_ghost))
+
+
 class SlabGroup:
     """The local ranks of one slab-decomposed simulation (1 with NCCL, all of them with LOCAL)."""
 
@@ -61,7 +76,7 @@ class SlabGroup:
         self._arr = (C.c_void_p * len(sims))(*[s._h for s in sims])
 
     @classmethod
-    def local(cls, world: int, stream: int = 0, **cfg_kw):
+    def local(cls, world: int, stream: int = 0, rebalance_every: int = 0, **cfg_kw):
         own = None
         if not stream:                  # all virtual ranks must share one stream
             import torch
@@ -71,7 +86,7 @@ class SlabGroup:
         sims[0]._shared_stream = own    # keep the stream object alive with the group
         for r, s in enumerate(sims):
             cfg = DistConfig(struct_size=C.sizeof(DistConfig), rank=r, world=world,
-                             transport=TRANSPORT_LOCAL)
+                             transport=TRANSPORT_LOCAL, rebalance_every=rebalance_every)
             s._ck(s.lib.nprsph_dist_init(s._h, C.byref(cfg)))
         g = cls(sims, TRANSPORT_LOCAL)
         rc = g.lib.nprsph_dist_link_local(g._arr, world)
@@ -80,11 +95,12 @@ class SlabGroup:
         return g
 
     @classmethod
-    def nccl(cls, rank: int, world: int, nccl_id: bytes, max_own=0, max_ghost=0, max_migrate=0, **cfg_kw):
+    def nccl(cls, rank: int, world: int, nccl_id: bytes, max_own=0, max_ghost=0, max_migrate=0,
+             rebalance_every=0, **cfg_kw):
         sim = B.Simulation(**cfg_kw)
         cfg = DistConfig(struct_size=C.sizeof(DistConfig), rank=rank, world=world,
                          transport=TRANSPORT_NCCL, max_own=max_own, max_ghost=max_ghost,
-                         max_migrate=max_migrate)
+                         max_migrate=max_migrate, rebalance_every=rebalance_every)
         C.memmove(cfg.nccl_id, nccl_id, 128)
         sim._ck(sim.lib.nprsph_dist_init(sim._h, C.byref(cfg)))
         return cls([sim], TRANSPORT_NCCL)

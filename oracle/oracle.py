@@ -125,7 +125,7 @@ def dam_break_params(nx: int, ny: int, nz: int, spacing: float = 0.005) -> Param
     p.smoothing_coeff = 2.0
     p.mass = 1.2379e-4
     p.visc = 50.0
-    p.gas_const = 200.0
+    p.gas_const = 2000.0           # the reference's own GAS_CONST (npr-sph_b200/scenes.py explains)
     p.gravity[0], p.gravity[1], p.gravity[2] = 0.0, -9.80665, 0.0
     p.dt = 1e-4
     lx, ly, lz = nx * s, ny * s, nz * s

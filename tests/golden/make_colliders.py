@@ -18,6 +18,7 @@ from oracle import oracle as O  # noqa: E402
 def scene():
     nx, s = 10, 0.005
     p = O.dam_break_params(nx, nx, nx)
+    p.gas_const = 200.0            # the fixture was frozen with the softer stiffness of SURVEY 8(d)
     cols = [("sphere", (0.07, 0.015, 0.03), 0.012), ("box", (0.05, -s, 0.0), (0.056, 0.02, 0.02))]
     P = O.jitter(O.make_block(nx, nx, nx), 0.2 * s, seed=21)
     P[:, 4] = 1.5

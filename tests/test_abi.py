@@ -22,7 +22,7 @@ def test_every_declared_symbol_is_exported_and_bound(sph):
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/nprsph.h but not exported"
     assert sorted(sph.binding.SYMBOLS) == names, "binding.py must mirror the header one to one"
-    assert lib.nprsph_abi_version() == 1
+    assert lib.nprsph_abi_version() == 2
 
 
 def test_pod_layouts_match_the_reference_structs(sph):

@@ -75,3 +75,59 @@ def test_slab_partition_properties(sph):
     # balanced when the histogram allows it
     b = slab_partition(np.full(64, 100, np.uint64), 4, 2)
     assert list(b) == [0, 16, 32, 48, 64]
+
+
+def _rebalance_worker(rank, world, port, out_dir):
+    """Each rank knows its own counter block, exchanges it with the neighbour over gloo (what the
+    per-step ncclSend/ncclRecv of 12 words does) and evaluates the face rule: both must agree."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nprsph_b200 import dist as D
+    rng = np.random.default_rng(7)
+    decisions = []
+    for trial in range(50):
+        layer = int(rng.integers(100, 5000))
+        blocks = np.zeros((world, D.SLAB_COUNTER_WORDS), np.uint32)
+        for r in range(world):
+            own = int(rng.integers(20, 200)) * layer
+            blocks[r, [D.CNT_HALO_L, D.CNT_HALO_R]] = 2 * layer
+            blocks[r, D.CNT_OWN], blocks[r, D.CNT_FREE] = own, int(rng.integers(0, 400)) * layer
+            blocks[r, D.CNT_WIDTH], blocks[r, D.CNT_CAP_MIGRATE] = own // layer, int(rng.integers(1, 8)) * layer
+        mine = torch.from_numpy(blocks[rank].astype(np.int64))
+        other = torch.zeros_like(mine)
+        peer = 1 - rank
+        ops = [dist.P2POp(dist.isend, mine, peer), dist.P2POp(dist.irecv, other, peer)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        theirs = other.numpy().astype(np.uint32)
+        assert np.array_equal(theirs, blocks[peer])
+        a, b = (blocks[rank], theirs) if rank == 0 else (theirs, blocks[rank])
+        decisions.append(D.slab_face_move(a, b, 2, 64 * layer))
+    np.save(os.path.join(out_dir, f"moves{rank}.npy"), np.array(decisions))
+    dist.destroy_process_group()
+
+
+def test_rebalancing_rule_agrees_across_ranks(tmp_path):
+    mp.spawn(_rebalance_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    m0, m1 = np.load(tmp_path / "moves0.npy"), np.load(tmp_path / "moves1.npy")
+    assert np.array_equal(m0, m1), "both ranks of a face must take the same decision"
+    assert set(m0.tolist()) == {-1, 0, 1}, "the random trials should exercise all three outcomes"
+
+
+def test_rebalancing_rule_properties(sph):
+    from nprsph_b200 import dist as D
+    def block(own, layer, free=10**7, width=40, cap_mig=10**6):
+        b = np.zeros(D.SLAB_COUNTER_WORDS, np.uint32)
+        b[[D.CNT_HALO_L, D.CNT_HALO_R]] = 2 * layer
+        b[D.CNT_OWN], b[D.CNT_FREE], b[D.CNT_WIDTH], b[D.CNT_CAP_MIGRATE] = own, free, width, cap_mig
+        return b
+    L = 1000
+    assert D.slab_face_move(block(50 * L, L), block(50 * L, L), 2, 10**6) == 0          # balanced
+    assert D.slab_face_move(block(50 * L, L), block(51 * L, L), 2, 10**6) == 0          # within two layers
+    assert D.slab_face_move(block(60 * L, L), block(40 * L, L), 2, 10**6) == -1         # left rank is heavier
+    assert D.slab_face_move(block(40 * L, L), block(60 * L, L), 2, 10**6) == +1
+    assert D.slab_face_move(block(60 * L, L, width=5), block(40 * L, L), 2, 10**6) == 0  # giver too narrow (2R+2 = 6)
+    assert D.slab_face_move(block(60 * L, L), block(40 * L, L, free=1000), 2, 10**6) == 0   # receiver full
+    assert D.slab_face_move(block(60 * L, L, cap_mig=1500), block(40 * L, L), 2, 10**6) == 0  # layer exceeds the migration buffer
+    assert D.slab_face_move(block(60 * L, L), block(40 * L, L), 2, 3 * L) == 0          # ... or the ghost capacity

@@ -300,3 +300,62 @@ def test_snapshot_restart_is_bit_exact(sph, oracle, tmp_path):
     (tmp_path / "junk").write_bytes(b"x" * 300)
     with pytest.raises(sph.NprSphError):
         b.load(tmp_path / "junk")
+
+
+def test_streaming_state_upload_and_position_download(sph, oracle):
+    """nprsph_upload_state (the inputs of a step: positions + velocities) and
+    nprsph_download_positions (what the renderer reads, attribute 0 of the records):
+    a run fed through them equals the run fed through the 64-byte records."""
+    nx = 18
+    p = oracle.dam_break_params(nx, nx, nx)
+    P = oracle.jitter(oracle.make_block(nx, nx, nx), 0.2 * 0.005, seed=3)
+    P[:, 3] = np.random.default_rng(1).normal(size=len(P)).astype(np.float32)    # the w lane is the caller's
+    a = sph.Simulation(cell_subdiv=2); a.apply_params(p); a.upload(P); a.set_paused(False)
+    b = sph.Simulation(cell_subdiv=2); b.apply_params(p); b.upload(P); b.set_paused(False)
+    for _ in range(3):
+        a.step(4)
+        A = a.download()
+        assert np.array_equal(a.download_positions().view(np.uint32), A[:, 0:4].view(np.uint32))
+        # restart b from a's state through the streaming interface: outputs read zero until the next step
+        b.upload_state(A[:, 0:4], A[:, 4:8])
+        B = b.download()
+        assert np.array_equal(B[:, 0:3], A[:, 0:3]) and np.array_equal(B[:, 4:7], A[:, 4:7])
+        assert np.array_equal(B[:, 3], P[:, 3]) and not B[:, 8:14].any()
+        a.upload(A)                      # (both restart from original particle order: same tie order in the sort)
+        a.step(1); b.step(1)
+        assert np.array_equal(a.download().view(np.uint32), b.download().view(np.uint32)), \
+            "force, density and pressure are outputs: the step after upload_state is the same step"
+        a.upload(A); b.upload(A)
+    with pytest.raises(sph.NprSphError):
+        b.upload_state(P[:5, 0:4], P[:5, 4:8])            # n must match the particle count
+
+
+def test_asynchronous_position_downloads_overlap_the_next_step(sph, oracle):
+    import torch
+    nx = 24
+    p = oracle.dam_break_params(nx, nx, nx)
+    sim = sph.Simulation(cell_subdiv=2); sim.apply_params(p)
+    sim.scene_block(nx, nx, nx, 0.005, None, 2e-4, 5); sim.set_paused(False)
+    n = sim.num_particles
+    bufs = [torch.empty(n * 4, dtype=torch.float32).pin_memory() for _ in range(3)]
+    want = []
+    for k in range(3):
+        sim.step(2)
+        sim.download_positions_ptr(bufs[k].data_ptr(), n, asynchronous=True)
+    sim.sync()
+    ref = sph.Simulation(cell_subdiv=2); ref.apply_params(p)
+    ref.scene_block(nx, nx, nx, 0.005, None, 2e-4, 5); ref.set_paused(False)
+    for k in range(3):
+        ref.step(2)
+        assert np.array_equal(bufs[k].view(n, 4).numpy(), ref.download()[:, 0:4]), k
+
+
+def test_walk_stats_agree_with_the_neighbour_counts(sph, oracle):
+    nx = 16
+    p = oracle.dam_break_params(nx, nx, nx)
+    P = oracle.jitter(oracle.make_block(nx, nx, nx), 0.3 * 0.005, seed=8)
+    sim = sph.Simulation(cell_subdiv=2, flags=sph.FLAG_COUNT_NEIGHBOURS); sim.apply_params(p); sim.upload(P)
+    st = sim.walk_stats()
+    c = oracle.pass_rho(P.copy(), p, counts=True)
+    assert st["neighbours"] == int(c.sum()) and st["distance_tests"] >= st["neighbours"]
+    assert 2 * st["pair_walks"] + st["single_walks"] == len(P)

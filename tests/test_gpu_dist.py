@@ -74,6 +74,11 @@ def test_migration_and_ghosts_under_strong_flow(sph, oracle):
         assert not np.isnan(G[:, POS]).any()
         assert_field_close(G[:, POS], A[:, POS], f"pos@{15 * (chunk + 1)}", elementwise=False)
         assert_field_close(G[:, RHO], A[:, RHO], f"rho@{15 * (chunk + 1)}", elementwise=False)
+        # force and pressure of a record belong to the same particle as its position (they are
+        # packed in the slot order of the step that computed them)
+        assert_field_close(G[:, FRC], A[:, FRC], f"force@{15 * (chunk + 1)}", elementwise=False)
+        assert_field_close(G[:, 13], A[:, 13], f"pressure@{15 * (chunk + 1)}", elementwise=False,
+                           scale=p.gas_const * (A[:, RHO] + p.resting_rho))
     moved = sum(grp.info(w).migrated_total for w in range(3))
     assert moved > 100, f"scene too static to exercise migration ({moved})"
     assert all(grp.info(w).ghosts_left + grp.info(w).ghosts_right > 0 for w in range(3))
@@ -134,3 +139,47 @@ def test_world_of_one_is_the_plain_step(sph, oracle):
     A, G = ref.download(), grp.gather(1000)
     assert np.array_equal(G[:, POS], A[:, POS]) and np.array_equal(G[:, RHO], A[:, RHO])
     grp.close()
+
+
+def test_rebalancing_moves_slab_faces_and_keeps_parity(sph, oracle):
+    """slab faces follow the fluid.  A strong horizontal flow piles particles up on the
+    downstream rank; with re-balancing every interior face moves one x layer at a time towards the
+    lighter rank, the layer travels through the ordinary migration path, and the result still
+    matches the single-context run."""
+    from nprsph_b200.dist import SlabGroup
+    nx, ny, nz = 48, 12, 10
+    p = _scene(oracle, nx, ny, nz, gy=-2.0)
+    p.gravity[0] = 300.0
+    n = nx * ny * nz
+    ref = sph.Simulation(cell_subdiv=2)
+    ref.apply_params(p)
+    ref.scene_block(nx, ny, nz, 0.005, None, 3e-4, 5)
+    ref.set_paused(False)
+    runs = {}
+    for every in (0, 4):
+        grp = SlabGroup.local(3, cell_subdiv=2, rebalance_every=every)
+        grp.apply_params(p)
+        grp.scene_block(nx, ny, nz, 0.005, None, 3e-4, 5)
+        grp.set_paused(False)
+        runs[every] = grp
+    for chunk in range(8):
+        ref.step(20)
+        A = ref.download()
+        for every, grp in runs.items():
+            grp.step(20)
+            G = grp.gather(n)
+            assert not np.isnan(G[:, POS]).any(), "every particle is held by exactly one rank"
+            for name, cols in (("pos", POS), ("vel", VEL), ("force", FRC), ("rho", RHO)):
+                assert_field_close(G[:, cols], A[:, cols], f"{name}@{20 * (chunk + 1)} rebalance_every={every}",
+                                   elementwise=False)
+    own = {e: [int(g.info(w).num_own) for w in range(3)] for e, g in runs.items()}
+    faces = {e: [(int(g.info(w).x_begin), int(g.info(w).x_end)) for w in range(3)] for e, g in runs.items()}
+    moves = sum(int(runs[4].info(w).rebalanced) for w in range(3))
+    print(f"\n[dist] own particles per rank after 160 steps: static {own[0]} faces {faces[0]}; "
+          f"re-balanced {own[4]} faces {faces[4]} ({moves} face moves)")
+    assert sum(own[0]) == n and sum(own[4]) == n
+    assert moves > 0 and faces[4] != faces[0]
+    assert all(faces[4][w][1] == faces[4][w + 1][0] for w in range(2)), "slabs must tile the x axis"
+    assert max(own[4]) - min(own[4]) < max(own[0]) - min(own[0]), "re-balancing must even out the ranks"
+    for g in runs.values():
+        g.close()

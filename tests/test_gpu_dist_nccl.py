@@ -43,7 +43,8 @@ def _worker(rank, world, port, out_dir, dims, steps):
     if rank == 0:
         idt.copy_(torch.frombuffer(bytearray(unique_id()), dtype=torch.uint8))
     dist.broadcast(idt, 0)
-    grp = SlabGroup.nccl(rank, world, idt.cpu().numpy().tobytes(), device=rank, cell_subdiv=2)
+    grp = SlabGroup.nccl(rank, world, idt.cpu().numpy().tobytes(), device=rank, cell_subdiv=2,
+                         rebalance_every=4)
     grp.apply_params(p)
     grp.scene_block(nx, ny, nz, 0.005, None, 2e-4, 21)
     grp.set_paused(False)
@@ -51,7 +52,7 @@ def _worker(rank, world, port, out_dir, dims, steps):
     rec, ids = grp.download()
     info = grp.info()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), rec=rec, ids=ids, migrated=info.migrated_total,
-             ghosts=info.ghosts_left + info.ghosts_right)
+             ghosts=info.ghosts_left + info.ghosts_right, rebalanced=info.rebalanced)
     if rank == 0:                                          # the same scene on one GPU
         ref = sph.Simulation(device=0, cell_subdiv=2)
         ref.apply_params(p)

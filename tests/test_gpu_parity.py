@@ -89,7 +89,7 @@ def check_passes(sim, sph, oracle, P, p, cell_subdiv, gpu_oracle=False):
     return ids
 
 
-@pytest.mark.parametrize("cell_subdiv", [1, 2])
+@pytest.mark.parametrize("cell_subdiv", [1, 2, 4])
 def test_config1_default_scene_pass_by_pass(sph, oracle, cell_subdiv):
     """BASELINE.json configs[0]: the reference's 10x100x10 block with its shader constants."""
     p = oracle.default_params()
@@ -128,7 +128,7 @@ def test_config1_steps_resynced_through_nan_onset(sph, oracle):
     assert sim.stats().nan_particles == np.isnan(P[:, POS]).any(axis=1).sum()
 
 
-@pytest.mark.parametrize("cell_subdiv", [1, 2])
+@pytest.mark.parametrize("cell_subdiv", [1, 2, 3])
 def test_dam_break_small_free_running(sph, oracle, cell_subdiv):
     """Stable dam-break recipe, 20x24x16 block, free running for 200 steps: the trajectory
     drift against the oracle stays bounded (reported in units of h)."""
@@ -188,7 +188,7 @@ def test_iterated_permutation_every_step(sph, oracle):
     assert moved > 0, "scene too static to exercise the re-sort"
 
 
-@pytest.mark.parametrize("cell_subdiv", [1, 2])
+@pytest.mark.parametrize("cell_subdiv", [1, 2, 3, 4])
 def test_ragged_sizes_and_degenerate_inputs(sph, oracle, cell_subdiv):
     p = oracle.dam_break_params(10, 10, 10)
     rng = np.random.default_rng(3)
@@ -321,3 +321,58 @@ def test_config3_sixteen_million_full_size(sph, oracle):
     sim.pass_integrate()
     oracle.pass_integrate(Q, p)
     assert_bits_equal(sim.download(), Q, "integrate must be bit-exact @16M")
+
+
+def step_vs_oracle(sim, sph, oracle, P, p, grid, tag):
+    """ONE nprsph_step (column records, deferred queues, fused force+integrate) from the host state P
+    against the oracle's step: neighbour counts of both passes bit-exact, fields to the tolerance."""
+    sim.upload(P)
+    sim.set_paused(False)
+    sim.step(1)
+    G = sim.download()
+    Q = P.copy()
+    c_rho = oracle.pass_rho(Q, p, counts=True, grid=grid)
+    c_f = oracle.pass_force(Q, p, counts=True, grid=grid)
+    oracle.pass_integrate(Q, p)
+    assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_RHO), c_rho), f"{tag}: density neighbour counts"
+    assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_FORCE), c_f), f"{tag}: force neighbour counts"
+    assert_field_close(G[:, RHO], Q[:, RHO], f"rho {tag}")
+    for name, cols in (("force", FRC), ("vel", VEL), ("pos", POS)):
+        assert_field_close(G[:, cols], Q[:, cols], f"{name} {tag}", elementwise=False)
+    return G
+
+
+@pytest.mark.parametrize("cell_subdiv", [0, 3, 4])
+def test_default_scene_whole_steps_replay_records_at_the_reference_smoothing(sph, oracle, cell_subdiv):
+    """BASELINE configs[0] through nprsph_step: at the reference's own h = 4 lattice spacings the
+    automatic grid (cell = h/4, 81 columns per walk) keeps every walk inside the column-record
+    format, so the force pass replays records instead of re-testing candidates."""
+    p = oracle.default_params()
+    sim = make_sim(sph, p, cell_subdiv)
+    assert sim.stats().cell_subdiv == (cell_subdiv or 4)
+    P = oracle.make_block(10, 100, 10)
+    for s in range(4):
+        P = step_vs_oracle(sim, sph, oracle, P, p, 1, f"default scene step {s} subdiv {cell_subdiv}")
+    if cell_subdiv in (0, 4):
+        st = sim.walk_stats()
+        assert st["pair_walks"] * 2 > 0.95 * len(P), st        # the lattice pairs up; almost nothing is deferred
+
+
+def test_config3_sixteen_million_evolved_whole_step(sph, oracle):
+    """BASELINE configs[2] AFTER the dam has broken (2,000 steps): one whole nprsph_step -- column
+    records, the deferred-slot kernels that carry a few percent of a disordered fluid, fused force +
+    integrate -- against the oracle's grid variant; the recipe must also have kept the 1.28 m column
+    free of NaNs."""
+    n1 = 256
+    p = oracle.dam_break_params(n1, n1, n1)
+    sim = make_sim(sph, p, 2)
+    sim.scene_block(n1, n1, n1, 0.005, None, 1e-4 * 0.005, 1234)
+    sim.set_paused(False)
+    sim.step(2000)
+    P = sim.download()
+    assert not np.isnan(P).any(), "dam-break recipe must keep the bench scene NaN-free"
+    st = sim.walk_stats()
+    assert st["single_walks"] > 0, "an evolved fluid has slots that cannot share a walk (deferred queue)"
+    step_vs_oracle(sim, sph, oracle, P, p, 2, "@16M evolved")
+    print(f"\n[evolved 16M] {st['single_walks']} deferred slots, {st['distance_tests'] / len(P):.1f} tests and "
+          f"{st['neighbours'] / len(P):.1f} neighbours per particle")

@@ -135,3 +135,18 @@ def test_collider_spec_of_the_oracle(oracle):
     assert P[2, 0] == np.float32(0.030) and P[2, 4] == np.float32(p.damping) and P[2, 5] == np.float32(0.5)
     # 3: identical to the collider-free pass
     assert np.array_equal(P[3], Q[3])
+
+
+def test_package_scene_recipes_equal_the_oracles(oracle):
+    """bench.py configures the product from npr-sph_b200/scenes.py (no oracle import on the product
+    arm); the parity tests use the oracle's copy.  The two must describe the same scenes."""
+    import nprsph_b200 as sph
+    pairs = [(sph.scenes.default_params(), oracle.default_params())]
+    for dims in ((256, 256, 256), (20, 24, 16), (512, 256, 512)):
+        pairs.append((sph.scenes.dam_break_params(*dims), oracle.dam_break_params(*dims)))
+    for a, b in pairs:
+        for k in ("mass", "smoothing_coeff", "visc", "resting_rho", "particle_radius", "gas_const", "damping", "dt", "pi"):
+            assert np.float32(getattr(a, k)) == np.float32(getattr(b, k)), k
+        for i in range(3):
+            assert np.float32(a.gravity[i]) == np.float32(b.gravity[i])
+            assert np.float32(a.upper[i]) == np.float32(b.upper[i]) and np.float32(a.lower[i]) == np.float32(b.lower[i])
