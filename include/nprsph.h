@@ -286,7 +286,7 @@ int nprsph_slab_partition(const uint64_t* hist, int dimx, int world, int min_wid
  * cell layer to the left: a hands its last layer to b), +1 (b hands its first layer to a) or 0. */
 #define NPRSPH_SLAB_COUNTER_WORDS 12
 enum { NPRSPH_CNT_LEAVE_L = 0, NPRSPH_CNT_LEAVE_R, NPRSPH_CNT_HALO_L, NPRSPH_CNT_HALO_R, NPRSPH_CNT_NAN,
-       NPRSPH_CNT_XMAX, NPRSPH_CNT_OWN, NPRSPH_CNT_FREE, NPRSPH_CNT_WIDTH, NPRSPH_CNT_CAP_MIGRATE };
+       NPRSPH_CNT_RESERVED, NPRSPH_CNT_OWN, NPRSPH_CNT_FREE, NPRSPH_CNT_WIDTH, NPRSPH_CNT_CAP_MIGRATE };
 int nprsph_slab_face_move(const uint32_t* a, const uint32_t* b, int reach, uint32_t cap_ghost);
 int nprsph_dist_unique_id(uint8_t id[128]);
 int nprsph_dist_init(nprsph_ctx* ctx, const nprsph_dist_config* cfg);

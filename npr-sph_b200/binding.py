@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnprsph.so")
+# (NPRSPH_LIB: an A/B build of the same library, `make VARIANT=...`; measurements only)
+LIB_PATH = os.environ.get("NPRSPH_LIB") or os.path.join(_HERE, "lib", "libnprsph.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED, ERR_COMM = -1, -2, -3, -4, -5, -6

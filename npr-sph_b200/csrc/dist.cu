@@ -193,8 +193,10 @@ k_gather_cells_slab(const uint32_t* __restrict__ sorted_keys, const uint32_t* __
                     const float4* __restrict__ frc_in, float4* __restrict__ frc_out, uint32_t n_frc, uint32_t n,
                     uint32_t n_valid, uint32_t slot_base, uint32_t tail_slot, uint32_t cell_lo,
                     uint32_t cell_hi, uint32_t* __restrict__ table, uint4* __restrict__ gap_list,
-                    uint32_t* __restrict__ gap_count) {
+                    uint32_t* __restrict__ gap_count, uint32_t plane, uint32_t* __restrict__ xmax_out) {
     const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    // top occupied x layer of this arrangement (keys are x-major): bounds next step's sort and table
+    if (s == 0) *xmax_out = n_valid ? sorted_keys[n_valid - 1u] / plane : 0u;
     if (s < n) {
         const uint32_t src = perm[s];
         pos_out[s] = pos_in[src];
@@ -536,10 +538,16 @@ int prepare_group(nprsph_ctx** cs, int n) {
         if (inL[r] + inR[r] > 2 * d->cap_mig || d->n_own + inL[r] + inR[r] > d->cap_own)
             return fail(c, NPRSPH_ERR_NOMEM, "own-particle capacity exceeded (raise max_own)%s");
         d->n_nan = mine[CNT_NAN];
-        {   // x layers the table must cover: occupied layers + reach; everything when the right
-            // side holds ghosts or immigrants
-            uint32_t top = mine[CNT_XMAX] + (uint32_t)d->R;
-            if (hasR || top > (uint32_t)d->lg.dim[0] - 1u) top = (uint32_t)d->lg.dim[0] - 1u;
+        {   // x layers the table and the sort must cover.  A rank with a right neighbour: all of them
+            // (ghosts and immigrants sit at the top).  The last rank owns the long empty stretch of box
+            // ahead of the dam break: the top occupied layer of the LAST sort (read off its last key by
+            // the gather kernel) + `reach` layers a particle may have moved since + `reach` layers the
+            // walks look ahead + 1 for a face that moved in between.
+            uint32_t top = (uint32_t)d->lg.dim[0] - 1u;
+            if (!hasR && d->xmax_known && !fp) {
+                const uint32_t t = errs[STICKY_XMAX] + 2u * (uint32_t)d->R + 1u;
+                if (t < top) top = t;
+            }
             d->x_top = top;
         }
         // boundary layers after migration: stayers + the immigrants that arrive through that face
@@ -612,7 +620,9 @@ int prepare_group(nprsph_ctx** cs, int n) {
                 c->pos[nxt] + d->own_off, c->vel[nxt] + d->own_off,
                 frc_tmp ? c->frc[0] + d->own_off : nullptr, frc_tmp, d->n_own, n_new,
                 n_new - d->n_nan, d->own_off,
-                d->own_off + n_new, (uint32_t)d->R * plane, own_hi, c->cell_start, c->gap_list, c->gap_count);
+                d->own_off + n_new, (uint32_t)d->R * plane, own_hi, c->cell_start, c->gap_list, c->gap_count,
+                plane, d->d_counts + 3 * CNT_WORDS + STICKY_XMAX);
+            d->xmax_known = true;
             if (frc_tmp && n_new)
                 CK(c, cudaMemcpyAsync(c->frc[0] + d->own_off, frc_tmp, (size_t)n_new * sizeof(float4),
                                       cudaMemcpyDeviceToDevice, c->stream));
@@ -920,6 +930,7 @@ int nprsph_dist_scene_block(nprsph_ctx* c, int nx, int ny, int nz, float spacing
     CK(c, cudaGetLastError());
     d->n_own = (uint32_t)n_cand;
     d->first_prepare = true;
+    d->xmax_known = false;
     d->gather_force = false;         // (the scene's force array is zero)
     d->prepared = false;
     d->classified = false;
@@ -1016,6 +1027,7 @@ int nprsph_dist_upload(nprsph_ctx* c, const nprsph_particle* records, const uint
         CK(c, cudaGetLastError());
     }
     d->n_own = (uint32_t)n;
+    d->xmax_known = false;
     d->first_prepare = false;        // a record of the slab next door is handed over by the next prepare
     d->gather_force = true;          // the uploaded force / pressure columns follow the re-sort
     d->prepared = false;

@@ -29,6 +29,7 @@ struct DistState {
     uint32_t cap_ghost = 0, cap_own = 0, cap_mig = 0, cap_total = 0, own_off = 0;
     uint32_t n_own = 0, n_nan = 0, gL = 0, gR = 0, hL = 0, hR = 0;
     uint32_t x_top = 0;                // highest local x cell layer any walk of this step can touch
+    bool xmax_known = false;           // the sticky word STICKY_XMAX holds the top occupied layer of the last sort
     bool first_prepare = true;         // candidates that belong to other ranks are dropped, not sent
     uint64_t migrated_total = 0, steps_done = 0;
     uint32_t last_migrated = 0;        // particles this rank handed over in the last prepare

@@ -15,7 +15,8 @@ enum { CNT_LEAVE_L = 0, CNT_LEAVE_R, CNT_HALO_L, CNT_HALO_R, CNT_NAN, CNT_XMAX,
        CNT_NOWN, CNT_FREE, CNT_WIDTH, CNT_CAPMIG,
        CNT_WORDS = 12 };
 // sticky error flags behind the three counter blocks (never cleared by the per-step memset)
-enum { ERR_IMMIGRANT = 0, ERR_OVERFLOW, ERR_WORDS = 8 };
+// (+ the top occupied x layer of the last sort, written by the gather kernel of every prepare)
+enum { ERR_IMMIGRANT = 0, ERR_OVERFLOW, STICKY_XMAX, ERR_WORDS = 8 };
 
 // Sentinel keys of the slab sort.  All high bits set, so a sort on the low b bits keeps them behind
 // every cell key (in this order) as long as the cell keys stay below 2^b - 4: the digit passes
@@ -60,8 +61,12 @@ __device__ __forceinline__ void send_leaver(uint32_t key, const float4& p, const
     }
 }
 
-// Boundary-layer / NaN counts and the top occupied layer for up to two freshly keyed own particles
-// per thread.  EVERY thread of the block calls it (KEY_NONE for a lane without a particle).
+// Boundary-layer / NaN counts for up to two freshly keyed own particles per thread.  EVERY lane of
+// the warp calls it (KEY_NONE for a lane without a particle); warp-level only, no block barrier.
+// (The top occupied x layer, which bounds the sort and the cell table of the last rank's long empty
+// stretch of box, is no longer reduced here -- half a million warps on one address cost more than
+// the rest of the kernel: the gather kernel reads it off the last sorted key, and a particle moves at
+// most `reach` layers per step, see prepare_group.)
 __device__ __forceinline__ void classify_counts(uint32_t ka, uint32_t kb, const SlabNext& sn) {
     const uint32_t plane = (uint32_t)sn.g.dim[1] * (uint32_t)sn.g.dim[2];
     const uint32_t xa = ka < KEY_NAN ? ka / plane : 0u, xb = kb < KEY_NAN ? kb / plane : 0u;
@@ -78,21 +83,10 @@ __device__ __forceinline__ void classify_counts(uint32_t ka, uint32_t kb, const 
         if (nR) atomicAdd(sn.counts + CNT_HALO_R, nR);
         if (nN) atomicAdd(sn.counts + CNT_NAN, nN);
     }
-    // highest occupied x layer: the cell table and the sort only have to reach `reach` layers
-    // beyond it (the last rank of a dam break owns a long empty stretch of the box).  Reduced per
-    // block and checked against the current value first: half a million warps hammering one L2
-    // address -- with an atomic or with a load -- cost more than the rest of the kernel.
-    __shared__ uint32_t s_xmax;
-    if (threadIdx.x == 0) s_xmax = 0u;
-    __syncthreads();
-    const uint32_t xm = __reduce_max_sync(0xffffffffu, max(xa, xb));
-    if (lane == 0 && xm) atomicMax(&s_xmax, xm);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_xmax > __ldcg(sn.counts + CNT_XMAX)) atomicMax(sn.counts + CNT_XMAX, s_xmax);
 }
 
-// One own particle's new key -> leaver into the migration buffer + the counts above.  EVERY thread
-// of the block calls it.
+// One own particle's new key -> leaver into the migration buffer + the counts above.  EVERY lane of
+// the warp calls it.
 __device__ __forceinline__ void classify_key(uint32_t key, const float4& p, const float4& v, const SlabNext& sn) {
     if (key == KEY_GONE_L || key == KEY_GONE_R) send_leaver(key, p, v, sn);
     classify_counts(key, KEY_NONE, sn);
@@ -107,7 +101,6 @@ __device__ __forceinline__ void classify_key_single(uint32_t key, const float4& 
     const uint32_t cxl = key / ((uint32_t)sn.g.dim[1] * (uint32_t)sn.g.dim[2]);
     if (cxl < (uint32_t)(2 * sn.R)) atomicAdd(sn.counts + CNT_HALO_L, 1u);
     if (cxl >= (uint32_t)sn.W) atomicAdd(sn.counts + CNT_HALO_R, 1u);
-    if (cxl > __ldcg(sn.counts + CNT_XMAX)) atomicMax(sn.counts + CNT_XMAX, cxl);
 }
 
 }  // namespace nprsph

@@ -326,8 +326,9 @@ def test_streaming_state_upload_and_position_download(sph, oracle):
         assert np.array_equal(a.download().view(np.uint32), b.download().view(np.uint32)), \
             "force, density and pressure are outputs: the step after upload_state is the same step"
         a.upload(A); b.upload(A)
+    few = np.ascontiguousarray(P[:5, 0:4])
     with pytest.raises(sph.NprSphError):
-        b.upload_state(P[:5, 0:4], P[:5, 4:8])            # n must match the particle count
+        b.upload_state_ptr(few.ctypes.data, few.ctypes.data, 5)      # n must match the particle count
 
 
 def test_asynchronous_position_downloads_overlap_the_next_step(sph, oracle):

@@ -169,9 +169,11 @@ def test_rebalancing_moves_slab_faces_and_keeps_parity(sph, oracle):
             grp.step(20)
             G = grp.gather(n)
             assert not np.isnan(G[:, POS]).any(), "every particle is held by exactly one rank"
-            for name, cols in (("pos", POS), ("vel", VEL), ("force", FRC), ("rho", RHO)):
+            # (immigrants join a cell behind its residents, so sums run in another order than on one
+            #  context; 160 steps of a violent flow amplify that rounding: the derived fields get 1e-4)
+            for name, cols, tol in (("pos", POS, 1e-5), ("rho", RHO, 1e-5), ("vel", VEL, 1e-4), ("force", FRC, 1e-4)):
                 assert_field_close(G[:, cols], A[:, cols], f"{name}@{20 * (chunk + 1)} rebalance_every={every}",
-                                   elementwise=False)
+                                   tol=tol, elementwise=False)
     own = {e: [int(g.info(w).num_own) for w in range(3)] for e, g in runs.items()}
     faces = {e: [(int(g.info(w).x_begin), int(g.info(w).x_end)) for w in range(3)] for e, g in runs.items()}
     moves = sum(int(runs[4].info(w).rebalanced) for w in range(3))
