@@ -198,7 +198,9 @@ class SingleRunner:
         self.dims = dims
         self.n_own = self.n_total = dims[0] * dims[1] * dims[2]
         self.p = sph.scenes.dam_break_params(*dims)
-        self.sim = sph.Simulation(device=local, stream=stream.cuda_stream, cell_subdiv=args.subdiv, flags=flags)
+        # (max_cells: the 64 Mi box has 4.0e8 cells of h/2; the default cap of 2^28 would enlarge them)
+        self.sim = sph.Simulation(device=local, stream=stream.cuda_stream, cell_subdiv=args.subdiv, flags=flags,
+                                  max_cells=1 << 30)
         self.sim.apply_params(self.p)
         self.sim.scene_block(*dims, SPACING, None, JITTER, SEED)
         self.sim.set_paused(False)
@@ -238,7 +240,7 @@ class SlabRunner:
             idt.copy_(torch.frombuffer(bytearray(unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         self.grp = SlabGroup.nccl(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local,
-                                  stream=stream.cuda_stream, cell_subdiv=args.subdiv,
+                                  stream=stream.cuda_stream, cell_subdiv=args.subdiv, max_cells=1 << 30,
                                   rebalance_every=args.rebalance_every)
         self.grp.apply_params(self.p)
         self.grp.scene_block(*dims, SPACING, None, JITTER, SEED)
@@ -581,12 +583,16 @@ def run_ours(args):
             if cdims == dims:
                 configs[name] = {"same_as": "main line"}
                 continue
+            twin = next((k for k, v in configs.items() if v.get("dims") == list(cdims)), None)
+            if twin:
+                configs[name] = {"same_as": twin, "scaling": kind}
+                continue
             r = make_runner(cdims)
             r.step(args.extra_evolve_steps)
             m0 = moved_so_far(r)
             k = max(5, min(args.steps, 20))
             ms = timed(r, stream, torch, k, 3, barrier, max_over_ranks)
-            configs[name] = {"workload": workload_name(cdims, args.extra_evolve_steps, world), "scaling": kind,
+            configs[name] = {"workload": workload_name(cdims, args.extra_evolve_steps, world), "scaling": kind, "dims": list(cdims),
                              "particles_total": r.n_total, "ms_per_step": round(ms, 4),
                              "value": r.n_total / (ms * 1e-3), "unit": UNIT, "steps": k,
                              "step_frac": round(192 * r.n_total / world / (ms * 1e-3) / 1e9 / peak, 4),
