@@ -63,9 +63,11 @@ def parse_args():
                     help="N > 1 main line: weak = side^3 per GPU; strong = BASELINE configs[3], 512x256x512 in total")
     ap.add_argument("--no-extra-configs", action="store_true",
                     help="skip the secondary BASELINE configs[3]/[4] sections")
-    ap.add_argument("--extra-evolve-steps", type=int, default=600)
+    ap.add_argument("--extra-evolve-steps", type=int, default=1200)
     ap.add_argument("--rebalance-every", type=int, default=8,
                     help="N > 1: slab faces may move one x layer every so many steps (0 = static slabs)")
+    ap.add_argument("--balance", default="time", choices=["time", "count"],
+                    help="N > 1: what re-balancing equalises: the measured time of the density pass or particle counts")
     return ap.parse_args()
 
 
@@ -241,7 +243,7 @@ class SlabRunner:
         dist.broadcast(idt, 0)
         self.grp = SlabGroup.nccl(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local,
                                   stream=stream.cuda_stream, cell_subdiv=args.subdiv, max_cells=1 << 30,
-                                  rebalance_every=args.rebalance_every)
+                                  rebalance_every=-args.rebalance_every if args.balance == "time" else args.rebalance_every)
         self.grp.apply_params(self.p)
         self.grp.scene_block(*dims, SPACING, None, JITTER, SEED)
         self.grp.set_paused(False)
@@ -258,7 +260,8 @@ class SlabRunner:
         self.launches_per_step = 14 + self.sort_passes
         self.fused = True
         self.parallelism = (f"{world} slabs along x, 1 process/GPU, ghost halo (pos; v,rho) + migration "
-                            f"via ncclSend/ncclRecv each step, faces re-balanced every {args.rebalance_every} steps")
+                            f"via ncclSend/ncclRecv each step, faces re-balanced every {args.rebalance_every} steps "
+                            f"by {'density-pass time' if args.balance == 'time' else 'particle count'}")
         self.api = "nprsph_dist_upload + nprsph_dist_step(1) + nprsph_dist_download, pinned host buffers"
 
     def step(self, k):

@@ -260,8 +260,9 @@ typedef struct nprsph_dist_config {
     uint64_t max_own;           /* capacities in particles; 0 = derived from the scene */
     uint64_t max_ghost;         /* per side */
     uint64_t max_migrate;       /* per side and step */
-    int32_t  rebalance_every;   /* > 0: every so many steps each interior slab face may move by one x
-                                   cell layer towards the lighter rank (0 = static slabs) */
+    int32_t  rebalance_every;   /* != 0: every |rebalance_every| steps each interior slab face may move by one
+                                   x cell layer towards the lighter rank; > 0 balances particle counts,
+                                   < 0 the measured time of the density pass (0 = static slabs) */
     int32_t  reserved;
 } nprsph_dist_config;
 
@@ -286,8 +287,11 @@ int nprsph_slab_partition(const uint64_t* hist, int dimx, int world, int min_wid
  * cell layer to the left: a hands its last layer to b), +1 (b hands its first layer to a) or 0. */
 #define NPRSPH_SLAB_COUNTER_WORDS 12
 enum { NPRSPH_CNT_LEAVE_L = 0, NPRSPH_CNT_LEAVE_R, NPRSPH_CNT_HALO_L, NPRSPH_CNT_HALO_R, NPRSPH_CNT_NAN,
-       NPRSPH_CNT_RESERVED, NPRSPH_CNT_OWN, NPRSPH_CNT_FREE, NPRSPH_CNT_WIDTH, NPRSPH_CNT_CAP_MIGRATE };
-int nprsph_slab_face_move(const uint32_t* a, const uint32_t* b, int reach, uint32_t cap_ghost);
+       NPRSPH_CNT_RESERVED, NPRSPH_CNT_OWN, NPRSPH_CNT_FREE, NPRSPH_CNT_WIDTH, NPRSPH_CNT_CAP_MIGRATE,
+       NPRSPH_CNT_COST_US /* smoothed duration of the rank's density pass, microseconds */ };
+/* by_time != 0: weigh the ranks by NPRSPH_CNT_COST_US instead of NPRSPH_CNT_OWN (the disordered front of
+ * a dam break costs more per particle than the bulk) */
+int nprsph_slab_face_move(const uint32_t* a, const uint32_t* b, int reach, uint32_t cap_ghost, int by_time);
 int nprsph_dist_unique_id(uint8_t id[128]);
 int nprsph_dist_init(nprsph_ctx* ctx, const nprsph_dist_config* cfg);
 int nprsph_dist_link_local(nprsph_ctx** ranks, int n);

@@ -120,7 +120,7 @@ SYMBOLS = {
     # multi-GPU (slab decomposition); the Python-side driver lives in dist.py
     "nprsph_slab_partition": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
                                         C.POINTER(C.c_int32)]),
-    "nprsph_slab_face_move": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.c_uint32]),
+    "nprsph_slab_face_move": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.c_uint32, C.c_int]),
     "nprsph_dist_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "nprsph_dist_init": (C.c_int, [_P, _P]),
     "nprsph_dist_link_local": (C.c_int, [C.POINTER(_P), C.c_int]),

@@ -247,8 +247,8 @@ k_integrate_slab(float4* __restrict__ posid, float4* __restrict__ velrho,
     classify_key(key, p, v, sn);
 }
 
-__global__ void k_set_words(uint32_t* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+__global__ void k_set_words(uint32_t* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) {
+    dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d; dst[4] = e;
 }
 
 __global__ void __launch_bounds__(TPB)
@@ -392,7 +392,8 @@ int reset_counts(nprsph_ctx* c) {
     DistState* d = c->dist;
     CK(c, cudaMemsetAsync(d->d_counts, 0, 3 * CNT_WORDS * sizeof(uint32_t), c->stream));
     k_set_words<<<1, 1, 0, c->stream>>>(d->d_counts + CNT_NOWN, d->n_own, d->cap_own - d->n_own,
-                                         (uint32_t)(d->X1_next - d->X0_next), d->cap_mig);
+                                         (uint32_t)(d->X1_next - d->X0_next), d->cap_mig,
+                                         (uint32_t)(d->cost_ms * 1000.0f));
     return NPRSPH_OK;
 }
 
@@ -458,9 +459,25 @@ static PhaseTrace g_trace;
 // next local grid and travels through the ordinary migration path of the next prepare.
 // a = counters of the left rank of the face, b = of the right rank.  Returns -1 (face moves left:
 // a gives its last layer to b), +1 (b gives its first layer to a) or 0.
-int face_move(const uint32_t* a, const uint32_t* b, int R, uint32_t cap_ghost) {
+// by_time: the weight of a rank is the measured duration of its density pass (CNT_COST, microseconds)
+// instead of its particle count -- the front of a dam break costs more per particle than the bulk.
+int face_move(const uint32_t* a, const uint32_t* b, int R, uint32_t cap_ghost, bool by_time) {
     const int64_t nA = a[CNT_NOWN], nB = b[CNT_NOWN];
     const int64_t layerA = (a[CNT_HALO_R] + R - 1) / R, layerB = (b[CNT_HALO_L] + R - 1) / R;   // particles per x layer at the face
+    if (by_time && a[CNT_COST] && b[CNT_COST] && nA > 0 && nB > 0) {
+        const int64_t wA = a[CNT_COST], wB = b[CNT_COST];
+        const int64_t lwA = wA * layerA / nA, lwB = wB * layerB / nB;       // cost of the layer at the face
+        const int64_t cap_mig = a[CNT_CAPMIG] < b[CNT_CAPMIG] ? a[CNT_CAPMIG] : b[CNT_CAPMIG];
+        const int wmin = 2 * R + 2;
+        auto fits = [&](int64_t layer, int64_t free_rx) {
+            return 2 * layer + 1024 <= cap_mig && 2 * layer + 65536 <= free_rx &&
+                   (int64_t)(R + 2) * layer * 3 / 2 <= (int64_t)cap_ghost;
+        };
+        // (3 layers of hysteresis: the times are measurements)
+        if (wA > wB + 3 * lwA + 1 && (int)a[CNT_WIDTH] >= wmin && fits(layerA, b[CNT_FREE])) return -1;
+        if (wB > wA + 3 * lwB + 1 && (int)b[CNT_WIDTH] >= wmin && fits(layerB, a[CNT_FREE])) return +1;
+        return 0;
+    }
     const int64_t cap_mig = a[CNT_CAPMIG] < b[CNT_CAPMIG] ? a[CNT_CAPMIG] : b[CNT_CAPMIG];
     const int wmin = 2 * R + 2;           // a slab keeps 2R layers after giving one away on EACH face
     auto fits = [&](int64_t layer, int64_t free_rx) {
@@ -512,6 +529,12 @@ int prepare_group(nprsph_ctx** cs, int n) {
                               cudaMemcpyDeviceToHost, c->stream));
     }
     for (int r = 0; r < n; r++) CK(cs[r], cudaStreamSynchronize(cs[r]->stream));
+    for (int r = 0; r < n; r++) {          // duration of the last density pass (its events have completed)
+        DistState* d = cs[r]->dist;
+        float ms = 0.f;
+        if (d->work_timed && cudaEventElapsedTime(&ms, d->ev_work0, d->ev_work1) == cudaSuccess)
+            d->cost_ms = d->cost_ms > 0.f ? 0.75f * d->cost_ms + 0.25f * ms : ms;
+    }
     g_trace.mark(cs, n, 0);
 
     // (2) sizes, migrant exchange
@@ -561,8 +584,8 @@ int prepare_group(nprsph_ctx** cs, int n) {
         d->last_migrated = leaveL[r] + leaveR[r];
         // faces of the prepare after this one (the coming step keys its particles against them)
         if (d->rebalance_every > 0 && !fp && d->steps_done > 0 && d->steps_done % (uint64_t)d->rebalance_every == 0) {
-            const int mL = hasL ? face_move(fromL, mine, d->R, d->cap_ghost) : 0;
-            const int mR = hasR ? face_move(mine, fromR, d->R, d->cap_ghost) : 0;
+            const int mL = hasL ? face_move(fromL, mine, d->R, d->cap_ghost, d->balance_time) : 0;
+            const int mR = hasR ? face_move(mine, fromR, d->R, d->cap_ghost, d->balance_time) : 0;
             d->X0_next = d->X0 + mL;
             d->X1_next = d->X1 + mR;
             d->rebalanced += (uint64_t)((mL != 0) + (mR != 0));
@@ -688,8 +711,11 @@ int step_group(nprsph_ctx** cs, int n, cudaEvent_t* ev = nullptr) {
     for (int r = 0; r < n; r++) {
         nprsph_ctx* c = cs[r]; DistState* d = c->dist;
         CK(c, cudaSetDevice(c->cfg.device));
+        CK(c, cudaEventRecord(d->ev_work0, c->stream));
         launch_rho(c->pos[c->cur], c->vel[c->cur], nullptr, c->cell_start, d->own_off, d->n_own, d->lg,
                    c->sph, nullptr, c->hitmask, d->cap_total, c->stream);
+        CK(c, cudaEventRecord(d->ev_work1, c->stream));
+        d->work_timed = true;
         float4* v = c->vel[c->cur];
         const uint32_t right0 = d->own_off + d->n_own - d->n_nan - d->hR;
         x[r] = {v + d->own_off, (d->rank > 0 ? d->hL : 0u) * sizeof(float4),
@@ -786,6 +812,8 @@ void nprsph::dist_destroy(nprsph_ctx* c) {
     if (d->h_counts) cudaFreeHost(d->h_counts);
     if (d->comm_stream) { cudaStreamSynchronize(d->comm_stream); cudaStreamDestroy(d->comm_stream); }
     if (d->ev_rho) cudaEventDestroy(d->ev_rho);
+    if (d->ev_work0) cudaEventDestroy(d->ev_work0);
+    if (d->ev_work1) cudaEventDestroy(d->ev_work1);
     if (d->ev_halo) cudaEventDestroy(d->ev_halo);
     delete d;
     c->dist = nullptr;
@@ -816,11 +844,12 @@ int nprsph_slab_partition(const uint64_t* hist, int dimx, int world, int min_wid
 }
 
 static_assert(NPRSPH_SLAB_COUNTER_WORDS == CNT_WORDS && NPRSPH_CNT_OWN == CNT_NOWN && NPRSPH_CNT_FREE == CNT_FREE &&
-              NPRSPH_CNT_WIDTH == CNT_WIDTH && NPRSPH_CNT_CAP_MIGRATE == CNT_CAPMIG && NPRSPH_CNT_HALO_R == CNT_HALO_R,
+              NPRSPH_CNT_WIDTH == CNT_WIDTH && NPRSPH_CNT_CAP_MIGRATE == CNT_CAPMIG && NPRSPH_CNT_HALO_R == CNT_HALO_R &&
+              NPRSPH_CNT_COST_US == CNT_COST,
               "public counter layout");
-int nprsph_slab_face_move(const uint32_t* a, const uint32_t* b, int reach, uint32_t cap_ghost) {
+int nprsph_slab_face_move(const uint32_t* a, const uint32_t* b, int reach, uint32_t cap_ghost, int by_time) {
     if (!a || !b || reach < 1) return 0;
-    return face_move(a, b, reach, cap_ghost);
+    return face_move(a, b, reach, cap_ghost, by_time != 0);
 }
 
 int nprsph_dist_unique_id(uint8_t id[128]) {
@@ -848,10 +877,15 @@ int nprsph_dist_init(nprsph_ctx* c, const nprsph_dist_config* cfg) {
     CK(c, cudaMemset(d->d_counts, 0, (3 * CNT_WORDS + ERR_WORDS) * sizeof(uint32_t)));
     CK(c, cudaMallocHost(&d->h_counts, (3 * CNT_WORDS + ERR_WORDS) * sizeof(uint32_t)));
     // (a decision sees the neighbours' counts of the step before: at least every second step)
-    d->rebalance_every = cfg->rebalance_every > 0 ? (cfg->rebalance_every < 2 ? 2 : cfg->rebalance_every) : 0;
+    // rebalance_every < 0: balance the measured time of the density pass instead of particle counts
+    d->balance_time = cfg->rebalance_every < 0;
+    { const int every = cfg->rebalance_every < 0 ? -cfg->rebalance_every : cfg->rebalance_every;
+      d->rebalance_every = every > 0 ? (every < 2 ? 2 : every) : 0; }
     CK(c, cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
     CK(c, cudaEventCreateWithFlags(&d->ev_rho, cudaEventDisableTiming));
     CK(c, cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming));
+    CK(c, cudaEventCreate(&d->ev_work0));
+    CK(c, cudaEventCreate(&d->ev_work1));
     if (cfg->transport == NPRSPH_TRANSPORT_NCCL && cfg->world > 1) {
         NcclApi* api = nccl();
         if (!api) return fail(c, NPRSPH_ERR_UNSUPPORTED, "libnccl.so.2 not found%s");

@@ -43,6 +43,10 @@ struct DistState {
     // between computes its keys against them)
     int X0_next = 0, X1_next = 0;
     int rebalance_every = 0;           // steps between re-balancing decisions (0 = static slabs)
+    bool balance_time = false;         // balance the measured density-pass time instead of particle counts
+    cudaEvent_t ev_work0 = nullptr, ev_work1 = nullptr;   // around the density pass of the last step
+    bool work_timed = false;
+    float cost_ms = 0.f;               // smoothed duration of the density pass (the rank's work per step)
     uint64_t rebalanced = 0;           // face moves so far (both faces of this rank)
     uint32_t* mig_ids = nullptr;       // [4][2*cap_mig] scratch: ids, iota, sorted ids, order
     void* mig_sort_ws = nullptr;

@@ -12,7 +12,7 @@ struct Migrant { float4 posid, velrho; };      // one particle changing rank (32
 // per-step counters, one block of CNT_WORDS per rank and exchanged with both neighbours
 enum { CNT_LEAVE_L = 0, CNT_LEAVE_R, CNT_HALO_L, CNT_HALO_R, CNT_NAN, CNT_XMAX,
        // written by the host (reset_counts) for the neighbours' re-balancing decision:
-       CNT_NOWN, CNT_FREE, CNT_WIDTH, CNT_CAPMIG,
+       CNT_NOWN, CNT_FREE, CNT_WIDTH, CNT_CAPMIG, CNT_COST,
        CNT_WORDS = 12 };
 // sticky error flags behind the three counter blocks (never cleared by the per-step memset)
 // (+ the top occupied x layer of the last sort, written by the gather kernel of every prepare)

@@ -54,16 +54,17 @@ def slab_partition(hist, world: int, min_width: int) -> np.ndarray:
 
 
 SLAB_COUNTER_WORDS = 12
-CNT_HALO_L, CNT_HALO_R, CNT_OWN, CNT_FREE, CNT_WIDTH, CNT_CAP_MIGRATE = 2, 3, 6, 7, 8, 9
+CNT_HALO_L, CNT_HALO_R, CNT_OWN, CNT_FREE, CNT_WIDTH, CNT_CAP_MIGRATE, CNT_COST_US = 2, 3, 6, 7, 8, 9, 10
 
 
-def slab_face_move(a, b, reach: int, cap_ghost: int) -> int:
+def slab_face_move(a, b, reach: int, cap_ghost: int, by_time: bool = False) -> int:
     """The re-balancing rule for the face between the ranks whose counter blocks are a (left) and b."""
     a = np.ascontiguousarray(a, np.uint32)
     b = np.ascontiguousarray(b, np.uint32)
     assert len(a) == len(b) == SLAB_COUNTER_WORDS
     u32p = C.POINTER(C.c_uint32)
-    return int(B.load().nprsph_slab_face_move(a.ctypes.data_as(u32p), b.ctypes.data_as(u32p), reach, cap_ghost))
+    return int(B.load().nprsph_slab_face_move(a.ctypes.data_as(u32p), b.ctypes.data_as(u32p), reach, cap_ghost,
+                                              int(by_time)))
 
 
 class SlabGroup:

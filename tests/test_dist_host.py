@@ -131,3 +131,21 @@ def test_rebalancing_rule_properties(sph):
     assert D.slab_face_move(block(60 * L, L), block(40 * L, L, free=1000), 2, 10**6) == 0   # receiver full
     assert D.slab_face_move(block(60 * L, L, cap_mig=1500), block(40 * L, L), 2, 10**6) == 0  # layer exceeds the migration buffer
     assert D.slab_face_move(block(60 * L, L), block(40 * L, L), 2, 3 * L) == 0          # ... or the ghost capacity
+
+
+def test_rebalancing_by_measured_time(sph):
+    """rebalance_every < 0: equal particle counts but unequal density-pass times (the disordered front
+    of a dam break) still move the face, towards the rank that takes longer."""
+    from nprsph_b200 import dist as D
+    def block(own, layer, cost_us):
+        b = np.zeros(D.SLAB_COUNTER_WORDS, np.uint32)
+        b[[D.CNT_HALO_L, D.CNT_HALO_R]] = 2 * layer
+        b[D.CNT_OWN], b[D.CNT_FREE], b[D.CNT_WIDTH], b[D.CNT_CAP_MIGRATE], b[D.CNT_COST_US] = own, 10**7, 40, 10**6, cost_us
+        return b
+    L = 65536
+    slow, fast = block(256 * L, L, 1950), block(256 * L, L, 1690)
+    assert D.slab_face_move(slow, fast, 2, 10**7) == 0                         # by count: balanced
+    assert D.slab_face_move(slow, fast, 2, 10**7, by_time=True) == -1          # the slow rank hands a layer over
+    assert D.slab_face_move(fast, slow, 2, 10**7, by_time=True) == +1
+    assert D.slab_face_move(block(256 * L, L, 1700), fast, 2, 10**7, by_time=True) == 0   # within 3 layers' worth
+    assert D.slab_face_move(block(256 * L, L, 0), fast, 2, 10**7, by_time=True) == 0      # no measurement yet: by count
