@@ -181,6 +181,11 @@ int nprsph_sync(nprsph_ctx* ctx);
 /* one pass at a time, regardless of the pause flag (glDispatchCompute of one program):
  * rho_pres_comp.glsl / force_comp.glsl / integrate_comp.glsl */
 int nprsph_pass_rho(nprsph_ctx* ctx);
+/* Deviation from force_comp.glsl:59 (which reads particles[].extras[1]): the pressures p_i, p_j are
+ * re-evaluated from the stored densities as max(gas_const * (rho - resting_rho), 0) with the CURRENT
+ * constants -- what nprsph_pass_rho stores -- and extras[1] is rewritten with that value.  Identical
+ * inside nprsph_step; differs only if the constants are edited between the two stand-alone passes or
+ * the caller uploads a pressure that is not the equation of state of the uploaded density. */
 int nprsph_pass_force(nprsph_ctx* ctx);
 int nprsph_pass_integrate(nprsph_ctx* ctx);
 void* nprsph_stream(const nprsph_ctx* ctx);     /* cudaStream_t the work is queued on */

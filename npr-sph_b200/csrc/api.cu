@@ -1046,8 +1046,18 @@ int nprsph_snapshot_load(nprsph_ctx* c, const char* path) {
     if (fread(ids, 4, h.n, f) != h.n || fread(rec, sizeof(nprsph_particle), h.n, f) != h.n) {
         rc = fail(c, NPRSPH_ERR_INVALID, "truncated snapshot %s", path); goto done;
     }
-    for (uint64_t s = 0; s < h.n; s++)
-        if (ids[s] >= h.n) { rc = fail(c, NPRSPH_ERR_INVALID, "corrupt slot table in %s", path); goto done; }
+    {   // the slot table must be a permutation of 0..n-1 (a duplicate would leave stale records behind)
+        uint8_t* seen = (uint8_t*)calloc((h.n + 7) / 8 + 1, 1);
+        if (!seen) { rc = fail(c, NPRSPH_ERR_NOMEM, "out of host memory%s"); goto done; }
+        bool ok = true;
+        for (uint64_t s = 0; s < h.n && ok; s++) {
+            const uint32_t id = ids[s];
+            ok = id < h.n && !(seen[id >> 3] & (1u << (id & 7)));
+            if (ok) seen[id >> 3] |= (uint8_t)(1u << (id & 7));
+        }
+        free(seen);
+        if (!ok) { rc = fail(c, NPRSPH_ERR_INVALID, "corrupt slot table in %s", path); goto done; }
+    }
     c->consts = h.consts; c->bounds = h.bounds;
     c->cfg.particle_radius = h.particle_radius; c->cfg.gas_const = h.gas_const;
     for (int a = 0; a < 3; a++) c->cfg.gravity[a] = h.gravity[a];

@@ -113,20 +113,22 @@ __device__ __forceinline__ float eos_pressure(float rho, const SphDev& s) {
 
 // ---- empty runs of the cell table -------------------------------------------------------------------------
 // A thread of the table builders fills short empty runs itself and queues the others for
-// k_fill_gaps (grid.cu): medium runs in gap_list (one thread block each), the few huge ones (the
-// empty stretch of box ahead of a dam break) in a small list every block works on together.
-// ctl words: [0] medium-run count, [1] huge-run count; huge entries start at word 8.
+// k_fill_gaps (grid.cu), one thread block per queue entry.  A long run (the empty stretch of box
+// ahead of a dam break, the empty upper half of every x plane of a deep scene) is cut into pieces of
+// GAP_PIECE cells, so no block ever writes more than 256 KB.  (Round 1 kept the "huge" runs in a
+// separate 64-entry list filled by the whole grid and let an overflow fall back to ONE block per run:
+// a 512-cell-deep scene has a huge run in every x plane, and the first NaN particle then sent its
+// 135-million-cell run to a single block -- 11.9 ms per step instead of 0.45.)
+// ctl words: [0] queue length; [4], [5] tail state of the single-context table (grid.cu).
 constexpr uint32_t GAP_INLINE = 64;          // runs up to this length are written by the finder
-constexpr uint32_t GAP_HUGE = 1u << 17;      // runs from this length on are filled by the whole grid
-constexpr uint32_t GAP_HUGE_MAX = 64;        // capacity of the huge-run list (overflow: medium list)
-constexpr size_t GAP_CTL_BYTES = 32 + GAP_HUGE_MAX * sizeof(uint4);
+constexpr uint32_t GAP_PIECE = 1u << 16;     // queue entries hold at most this many cells
+constexpr size_t GAP_CTL_BYTES = 32;
 __device__ __forceinline__ void push_gap(uint32_t lo, uint32_t len, uint32_t slot,
                                          uint4* __restrict__ gap_list, uint32_t* __restrict__ ctl) {
-    if (len >= GAP_HUGE) {
-        const uint32_t k = atomicAdd(ctl + 1, 1u);
-        if (k < GAP_HUGE_MAX) { reinterpret_cast<uint4*>(ctl + 8)[k] = make_uint4(lo, len, slot, 0u); return; }
-    }
-    gap_list[atomicAdd(ctl, 1u)] = make_uint4(lo, len, slot, 0u);
+    const uint32_t pieces = (len + GAP_PIECE - 1u) / GAP_PIECE;
+    uint32_t k = atomicAdd(ctl, pieces);
+    for (uint32_t o = 0; o < len; o += GAP_PIECE, ++k)
+        gap_list[k] = make_uint4(lo + o, min(GAP_PIECE, len - o), slot, 0u);
 }
 
 // ---- pass 3 for one particle ----------------------------------------------------------------------------

@@ -913,6 +913,9 @@ int nprsph_dist_scene_block(nprsph_ctx* c, int nx, int ny, int nz, float spacing
         return fail(c, NPRSPH_ERR_INVALID, "bad block%s");
     int rc = refresh_params(c);
     if (rc) return rc;
+    // every rank generates only the lattice planes within one cell of its slab: a jitter of a cell or
+    // more could move a particle into a slab whose rank never generated it
+    if (!(jitter < c->cell_size)) return fail(c, NPRSPH_ERR_INVALID, "slab scene: jitter must stay below one grid cell%s");
     const float o[3] = {origin ? origin[0] : 0.f, origin ? origin[1] : 0.f, origin ? origin[2] : 0.f};
     // every rank derives the same count-balanced slab boundaries from the lattice planes
     const GridDev& g = c->grid;

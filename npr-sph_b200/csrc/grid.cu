@@ -111,13 +111,16 @@ k_reorder_cells(const uint32_t* __restrict__ sorted_keys, const uint32_t* __rest
     }
     const uint32_t lo = (s == 0) ? 0u : sorted_keys[s - 1] + 1u;
     if (key_here < lo) return;                    // same cell as the previous slot
-    if (s == n) {
-        // Tail (every cell above the last key holds n).  In a dam break that is most of the table;
-        // tail_state = {F, V} records that cells >= F already hold V from an earlier step, so only
-        // the cells the fluid vacated since then are rewritten.
+    if (key_here >= num_cells && lo <= num_cells) {
+        // Tail: the first slot that lies in no cell (the first NaN particle, or n when there is none)
+        // owns every cell above the last real key, up to num_cells.  In a dam break that is most of
+        // the table; tail_state = {F, V} records that cells F..num_cells already hold V from an
+        // earlier step, so only the cells the fluid vacated since then are rewritten.
+        if (s == n) cell_start[num_cells + 1u] = n;
         const uint32_t F = tail_state[0], V = tail_state[1];
-        tail_state[0] = lo; tail_state[1] = n;
-        if (V == n) {
+        tail_state[0] = lo; tail_state[1] = s;
+        key_here = num_cells;
+        if (V == s) {
             if (F <= lo) return;
             if (F <= key_here) key_here = F - 1u;
         }
@@ -130,19 +133,11 @@ k_reorder_cells(const uint32_t* __restrict__ sorted_keys, const uint32_t* __rest
     }
 }
 
-// Medium runs: one thread block each, round robin (an evolved dam break has ~10^5 of them; with
-// every block looping over the whole list this kernel took longer than the gather).  Huge runs:
-// all blocks together.
+// One thread block per queue entry, round robin (an evolved dam break has ~10^5 of them; with
+// every block looping over the whole list this kernel took longer than the gather).
 __global__ void __launch_bounds__(TPB)
 k_fill_gaps(const uint4* __restrict__ gap_list, const uint32_t* __restrict__ gap_count,
             uint32_t* __restrict__ cell_start) {
-    const uint32_t huge = min(gap_count[1], GAP_HUGE_MAX);
-    const uint4* huge_list = reinterpret_cast<const uint4*>(gap_count + 8);
-    const uint32_t stride = gridDim.x * TPB;
-    for (uint32_t gi = 0; gi < huge; gi++) {
-        const uint4 g = huge_list[gi];
-        for (uint32_t o = blockIdx.x * TPB + threadIdx.x; o < g.y; o += stride) cell_start[g.x + o] = g.z;
-    }
     const uint32_t gaps = gap_count[0];
     for (uint32_t gi = blockIdx.x; gi < gaps; gi += gridDim.x) {
         const uint4 g = gap_list[gi];
@@ -205,9 +200,11 @@ void launch_keys(const float4* posid, uint32_t* keys, uint32_t n, const GridDev&
 }
 
 size_t gap_list_capacity(uint32_t num_cells, uint64_t n) {
+    // a queued run is longer than GAP_INLINE and there is at most one run per slot (+ the tail); cutting
+    // the long ones into pieces adds at most num_cells / GAP_PIECE entries
     uint64_t by_cells = ((uint64_t)num_cells + 2) / (GAP_INLINE + 1) + 2;
     uint64_t by_n = n + 1;
-    return (size_t)(by_cells < by_n ? by_cells : by_n);
+    return (size_t)((by_cells < by_n ? by_cells : by_n) + ((uint64_t)num_cells + 2) / GAP_PIECE + 2);
 }
 
 void launch_reorder_cells(const uint32_t* sorted_keys, const uint32_t* perm, const float4* pos_in,

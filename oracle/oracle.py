@@ -93,6 +93,8 @@ def lib():
         for name in ("oracle_pass_rho_grid", "oracle_pass_force_grid"):
             getattr(L, name).argtypes = [fp, C.c_int, pp, C.c_int, u32p]
             getattr(L, name).restype = C.c_int
+        L.oracle_force_scale_grid.argtypes = [fp, C.c_int, pp, C.c_int, fp]
+        L.oracle_force_scale_grid.restype = C.c_int
         L.oracle_step_grid.argtypes = [fp, C.c_int, pp, C.c_int, C.c_int]
         L.oracle_step_grid.restype = C.c_int
         L.oracle_num_threads.restype = C.c_int
@@ -174,10 +176,14 @@ def pass_force(P, p, counts=False, grid=0):
     return c
 
 
-def force_scale(P, p) -> np.ndarray:
+def force_scale(P, p, grid=0) -> np.ndarray:
     """Sum of |terms| of the force sums, shape (n, 3); P must hold rho/p (after pass_rho)."""
     out = np.empty((len(P), 3), np.float32)
-    lib().oracle_force_scale(_fp(P), len(P), C.byref(p), _fp(out))
+    if grid:
+        rc = lib().oracle_force_scale_grid(_fp(P), len(P), C.byref(p), grid, _fp(out))
+        assert rc == 0, rc
+    else:
+        lib().oracle_force_scale(_fp(P), len(P), C.byref(p), _fp(out))
     return out
 
 

@@ -510,6 +510,40 @@ int oracle_pass_force_grid(float* P, int n, const oracle_params* p, int k, uint3
     return 0;
 }
 
+/* oracle_force_scale over the grid's candidate lists (same terms: a candidate that fails the
+ * predicate contributes nothing), for scenes too large for the all-pairs loop. */
+int oracle_force_scale_grid(const float* P, int n, const oracle_params* p, int k, float* scale3) {
+    oracle_grid g; cell_lists L;
+    if (oracle_grid_setup(p, k, 0, &g)) return -1;
+    if (build_lists(P, n, &g, &L)) return -2;
+    const float h = oracle_smoothing_length(p);
+    const float h6 = pow_once(h, 6);
+    const float spiky = -45.0f / (p->pi * h6);
+    const float lap = 45.0f / (p->pi * h6);
+#pragma omp parallel
+    {
+        int32_t* buf = NULL; int cap = 0;
+#pragma omp for schedule(dynamic, 256)
+        for (int i = 0; i < n; i++) {
+            const float* pi_ = P + (size_t)i * ORACLE_REC;
+            int m = gather_candidates(i, &L, &g, &buf, &cap);
+            double acc[3] = {0, 0, 0};
+            for (int s = 0; s < m; s++) {
+                if (buf[s] == i) continue;
+                force_acc a; memset(&a, 0, sizeof a);
+                if (force_term(pi_, P + (size_t)buf[s] * ORACLE_REC, h, p->mass, spiky, lap, &a))
+                    for (int q = 0; q < 3; q++)
+                        acc[q] += fabs((double)a.pres[q]) + fabs((double)a.visc[q] * p->visc);
+            }
+            for (int q = 0; q < 3; q++)
+                scale3[3 * (size_t)i + q] = (float)(acc[q] + fabs((double)pi_[12] * p->gravity[q]));
+        }
+        free(buf);
+    }
+    free_lists(&L);
+    return 0;
+}
+
 int oracle_step_grid(float* P, int n, const oracle_params* p, int k, int n_steps) {
     for (int s = 0; s < n_steps; s++) {
         int rc = oracle_pass_rho_grid(P, n, p, k, NULL);

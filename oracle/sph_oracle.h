@@ -93,6 +93,8 @@ int  oracle_pass_rho_grid(float* particles, int n, const oracle_params* p, int c
                           uint32_t* counts);
 int  oracle_pass_force_grid(float* particles, int n, const oracle_params* p, int cell_subdiv,
                             uint32_t* counts);
+int  oracle_force_scale_grid(const float* particles, int n, const oracle_params* p, int cell_subdiv,
+                             float* scale3);
 int  oracle_step_grid(float* particles, int n, const oracle_params* p, int cell_subdiv,
                       int n_steps);
 

@@ -300,6 +300,11 @@ def test_snapshot_restart_is_bit_exact(sph, oracle, tmp_path):
     (tmp_path / "junk").write_bytes(b"x" * 300)
     with pytest.raises(sph.NprSphError):
         b.load(tmp_path / "junk")
+    raw = bytearray(path.read_bytes())
+    raw[256 + 4:256 + 8] = raw[256:256 + 4]                       # slot table no longer a permutation
+    (tmp_path / "dup").write_bytes(bytes(raw))
+    with pytest.raises(sph.NprSphError):
+        b.load(tmp_path / "dup")
 
 
 def test_streaming_state_upload_and_position_download(sph, oracle):

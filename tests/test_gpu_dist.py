@@ -185,3 +185,15 @@ def test_rebalancing_moves_slab_faces_and_keeps_parity(sph, oracle):
     assert max(own[4]) - min(own[4]) < max(own[0]) - min(own[0]), "re-balancing must even out the ranks"
     for g in runs.values():
         g.close()
+
+
+def test_slab_scene_rejects_a_jitter_of_a_cell_or_more(sph, oracle):
+    """Every rank generates only the lattice planes next to its slab; a larger jitter could lose particles."""
+    from nprsph_b200.dist import SlabGroup
+    grp = SlabGroup.local(2, cell_subdiv=2)
+    grp.apply_params(_scene(oracle, 20, 8, 8))
+    with pytest.raises(sph.NprSphError):
+        grp.scene_block(20, 8, 8, 0.005, None, 0.006, 1)
+    grp.scene_block(20, 8, 8, 0.005, None, 0.002, 1)
+    assert sum(grp.download(w)[1].size for w in range(2)) == 20 * 8 * 8
+    grp.close()
