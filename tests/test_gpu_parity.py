@@ -324,25 +324,28 @@ def test_config3_sixteen_million_full_size(sph, oracle):
 
 
 def step_vs_oracle(sim, sph, oracle, P, p, grid, tag):
-    """ONE nprsph_step (column records, deferred queues, fused force+integrate) from the host state P
-    against the oracle's step: neighbour counts of both passes bit-exact, fields to the tolerance."""
+    """ONE nprsph_step (column records, deferred queues, fused force + integrate) from the host state
+    P, checked pass by pass on the step's OWN intermediate results: the oracle's density pass on P;
+    its force pass on P carrying the GPU's density (a stiff equation of state turns a 1e-5 density
+    difference into a 5e-4 pressure difference, so a force computed from the oracle's density is not
+    comparable); its integrate pass on the GPU's force, which must then match bit for bit."""
     sim.upload(P)
     sim.set_paused(False)
     sim.step(1)
     G = sim.download()
     Q = P.copy()
     c_rho = oracle.pass_rho(Q, p, counts=True, grid=grid)
-    scale = oracle.force_scale(Q, p, grid=grid)      # conditioning scale of the (cancelling) force sums
-    c_f = oracle.pass_force(Q, p, counts=True, grid=grid)
-    oracle.pass_integrate(Q, p)
     assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_RHO), c_rho), f"{tag}: density neighbour counts"
-    assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_FORCE), c_f), f"{tag}: force neighbour counts"
     assert_field_close(G[:, RHO], Q[:, RHO], f"rho {tag}")
-    # (whole step: the force pass sees the GPU's own density, so the norm gates apply, against the
-    #  conditioning scale -- a stiff fluid at rest is a sum of large cancelling terms)
-    assert_field_close(G[:, FRC], Q[:, FRC], f"force {tag}", scale=scale, elementwise=False)
-    for name, cols in (("vel", VEL), ("pos", POS)):
-        assert_field_close(G[:, cols], Q[:, cols], f"{name} {tag}", elementwise=False)
+    assert_field_close(G[:, PRS], Q[:, PRS], f"pressure {tag}", scale=p.gas_const * (np.abs(Q[:, RHO]) + p.resting_rho))
+    Q[:, RHO], Q[:, PRS] = G[:, RHO], G[:, PRS]            # identical inputs for the force pass
+    scale = oracle.force_scale(Q, p, grid=grid)
+    c_f = oracle.pass_force(Q, p, counts=True, grid=grid)
+    assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_FORCE), c_f), f"{tag}: force neighbour counts"
+    assert_field_close(G[:, FRC], Q[:, FRC], f"force {tag}", scale=scale)
+    Q[:, FRC] = G[:, FRC]                                  # identical inputs for the integrate pass
+    oracle.pass_integrate(Q, p)
+    assert_bits_equal(G, Q, f"{tag}: the fused integrate epilogue must be bit-exact")
     return G
 
 
