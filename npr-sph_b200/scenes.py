@@ -41,7 +41,7 @@ DEFAULT_BLOCK = (10, 100, 10)
 # h = 2 lattice spacings with a stiffness of 200 (sound speed 14 m/s).  That is too soft for the 1.28 m
 # column of the 16 Mi scene: the collapse reaches 4-5 m/s, i.e. Mach 0.3 -- densities of 1.45 rho0 and
 # particles pressed onto the same wall corner (normalize(0) = NaN; 60 NaN particles after 4,000 steps
-# of a thin slice of the column, scripts/recipe_stability.py).  SURVEY 8(d) says to raise the stiffness
+# of a thin slice of the column, tests/tools/recipe_stability.py).  SURVEY 8(d) says to raise the stiffness
 # for blocks taller than ~1 m; the recipe now keeps the reference's own GAS_CONST
 # (rho_pres_comp.glsl:33): sound speed 44.7 m/s, compression <= 4.4 %, no NaN in 3,250+ steps of the
 # same slice, wall impact of the front included.

@@ -2,9 +2,9 @@ import sys, json
 import numpy as np
 sys.path.insert(0, ".")
 import nprsph_b200 as sph
-from oracle import oracle as O
+
 side=128
-p = O.dam_break_params(side, side, side)
+p = sph.scenes.dam_break_params(side, side, side)
 sim = sph.Simulation(cell_subdiv=2, flags=sph.FLAG_COUNT_NEIGHBOURS)
 sim.apply_params(p)
 sim.scene_block(side, side, side, 0.005, None, 1e-4 * 0.005, 1234)

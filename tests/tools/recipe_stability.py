@@ -1,12 +1,12 @@
 """Stability probe of the dam-break parameter recipe on the CPU oracle (grid-accelerated, bit-identical
 to the all-pairs loop): a thin slice of the bench column (same height, smaller cross-section).
 
-    python scripts/recipe_stability.py NX NY NZ GAS_CONST DT STEPS [VISC]
+    python tests/tools/recipe_stability.py NX NY NZ GAS_CONST DT STEPS [VISC]
 
 Prints NaN count, density range and max speed every 250 steps."""
 import sys, time
 import numpy as np
-sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 from oracle import oracle as O
 
 nx, ny, nz = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
