@@ -105,7 +105,13 @@ int nprsph::effective_subdiv(const nprsph_ctx* c) {
 
 int nprsph::ensure_records(nprsph_ctx* c, uint64_t slots, int reach) {
     size_t need = 0;
-    if (!(c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) && slots && records_fit(reach, slots))
+    // A column record holds 16 hit bits per target.  With cells much larger than the lattice spacing
+    // (the GUI's smoothing slider, 7..10 radii, at the finest subdivision 4: 5-15 particles per cell)
+    // every column of every walk overflows: the density pass would write records nobody can use and the
+    // whole force pass would run as re-tests out of the deferred queue.  Then there are no records at
+    // all and both passes take their plain paths (k_rho without records, k_force_scan with a full grid).
+    const bool cells_too_coarse = c->consts.smoothing_coeff > 1.5f * (float)effective_subdiv(c);
+    if (!(c->cfg.flags & NPRSPH_FLAG_NO_HITMASK) && slots && records_fit(reach, slots) && !cells_too_coarse)
         need = rec_buffer_words(slots, rec_cols_of(reach));
     if (need == c->hitmask_words) return NPRSPH_OK;
     CK(c, cudaStreamSynchronize(c->stream));

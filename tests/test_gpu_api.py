@@ -258,19 +258,33 @@ def test_fused_force_integrate_step_is_bit_identical_to_the_three_pass_step(sph,
     assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
 
 
-def test_dense_clump_overflows_the_hitmask_gracefully(sph, oracle):
-    """More candidates than the bitmask holds (reference default scene: ~1700 per particle with
-    h = 4s at 160x rest density) must fall back to the re-test path with identical results."""
+@pytest.mark.parametrize("coeff", [3.0, 4.0])
+def test_dense_clump_overflows_the_hitmask_gracefully(sph, oracle, coeff):
+    """More candidates per column than a record's hit bits hold.  h = 3 lattice spacings on cells of
+    h/2: every walk overflows and each target is re-tested out of the deferred queue (REC_RESCAN);
+    h = 4 spacings on cells of h/2: the host does not even allocate records (cells too coarse) and
+    both passes take their plain paths.  Identical neighbour sets either way, whole step included."""
     p = oracle.default_params()
+    p.smoothing_coeff = coeff
     P = oracle.make_block(10, 100, 10)
     sim = sph.Simulation(cell_subdiv=2, flags=sph.FLAG_COUNT_NEIGHBOURS)
+    sim.apply_params(p)
     sim.upload(P)
     sim.pass_rho()
     sim.pass_force()
-    c = oracle.pass_rho(P, p, counts=True)
-    cf = oracle.pass_force(P, p, counts=True)
+    Q = P.copy()
+    c = oracle.pass_rho(Q, p, counts=True)
+    cf = oracle.pass_force(Q, p, counts=True)
     assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_RHO), c)
     assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_FORCE), cf)
+    sim.upload(P)
+    sim.set_paused(False)
+    sim.step(1)                                           # records (or none) -> fused / plain force + integrate
+    assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_RHO), c)
+    assert np.array_equal(sim.debug_read(sph.DBG_COUNTS_FORCE), cf)
+    oracle.pass_integrate(Q, p)
+    G = sim.download()
+    assert np.abs(G[:, 0:3] - Q[:, 0:3]).max() < 1e-6
 
 
 def test_snapshot_restart_is_bit_exact(sph, oracle, tmp_path):
