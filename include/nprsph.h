@@ -289,7 +289,9 @@ int nprsph_slab_partition(const uint64_t* hist, int dimx, int world, int min_wid
  * rebalance_every steps).  a / b = the per-step counter blocks of the rank left / right of the face,
  * NPRSPH_SLAB_COUNTER_WORDS words each: both ranks hold both blocks after the step's counter
  * exchange, so they decide alike without further communication.  Returns -1 (the face moves one x
- * cell layer to the left: a hands its last layer to b), +1 (b hands its first layer to a) or 0. */
+ * cell layer to the left: a hands its last layer to b), +1 (b hands its first layer to a) or 0.
+ * Faces only move with reach >= 2 (cell_subdiv >= 2): the receiver's boundary layer must hold the layer
+ * handed over AND the particles that cross the old face in the same step. */
 #define NPRSPH_SLAB_COUNTER_WORDS 12
 enum { NPRSPH_CNT_LEAVE_L = 0, NPRSPH_CNT_LEAVE_R, NPRSPH_CNT_HALO_L, NPRSPH_CNT_HALO_R, NPRSPH_CNT_NAN,
        NPRSPH_CNT_RESERVED, NPRSPH_CNT_OWN, NPRSPH_CNT_FREE, NPRSPH_CNT_WIDTH, NPRSPH_CNT_CAP_MIGRATE,

@@ -462,6 +462,10 @@ static PhaseTrace g_trace;
 // by_time: the weight of a rank is the measured duration of its density pass (CNT_COST, microseconds)
 // instead of its particle count -- the front of a dam break costs more per particle than the bulk.
 int face_move(const uint32_t* a, const uint32_t* b, int R, uint32_t cap_ghost, bool by_time) {
+    // With reach 1 (cell = h) the receiver's boundary layer is ONE cell layer: the layer handed over
+    // fills it, and a particle that crosses the old face in the same step would land one layer deeper
+    // than the halo accounting allows.  Faces only move when the boundary layer has room for both.
+    if (R < 2) return 0;
     const int64_t nA = a[CNT_NOWN], nB = b[CNT_NOWN];
     const int64_t layerA = (a[CNT_HALO_R] + R - 1) / R, layerB = (b[CNT_HALO_L] + R - 1) / R;   // particles per x layer at the face
     if (by_time && a[CNT_COST] && b[CNT_COST] && nA > 0 && nB > 0) {

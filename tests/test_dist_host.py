@@ -131,6 +131,7 @@ def test_rebalancing_rule_properties(sph):
     assert D.slab_face_move(block(60 * L, L), block(40 * L, L, free=1000), 2, 10**6) == 0   # receiver full
     assert D.slab_face_move(block(60 * L, L, cap_mig=1500), block(40 * L, L), 2, 10**6) == 0  # layer exceeds the migration buffer
     assert D.slab_face_move(block(60 * L, L), block(40 * L, L), 2, 3 * L) == 0          # ... or the ghost capacity
+    assert D.slab_face_move(block(60 * L, L), block(40 * L, L), 1, 10**6) == 0          # reach 1: no room in the boundary layer
 
 
 def test_rebalancing_by_measured_time(sph):
