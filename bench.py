@@ -668,6 +668,30 @@ def all_pairs_sample(O, host, q, budget_s):
     return m / dt, m, dt
 
 
+def egl_reference_run():
+    """the reference's unmodified compute shaders run headless through EGL on this
+    box's GPU (tools/egl_shader_runner.c), where the driver exposes GL and a checkout of the reference
+    is named by NPRSPH_REFERENCE_SHADERS.  Reports why not otherwise."""
+    import tempfile
+    src = os.path.join(ROOT, "tools", "egl_shader_runner.c")
+    shaders = os.environ.get("NPRSPH_REFERENCE_SHADERS", "")
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            exe = os.path.join(tmp, "egl_shader_runner")
+            subprocess.check_call(["gcc", "-O2", "-std=c99", src, "-o", exe, "-ldl"], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+            r = subprocess.run([exe, shaders or os.path.join(tmp, "no-reference-checkout"), "200"], capture_output=True,
+                               text=True, timeout=120)
+    except (OSError, subprocess.SubprocessError) as e:
+        return {"unavailable": f"runner did not build or run: {e}"}
+    if r.returncode == 0:
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    why = (r.stderr.strip().splitlines() or ["exit %d" % r.returncode])[-1]
+    if r.returncode != 3 and not shaders:
+        why = "EGL context available, but NPRSPH_REFERENCE_SHADERS does not name a checkout of the reference's NPR-SPH directory"
+    return {"unavailable": why}
+
+
 def cpu_baselines(host, p, subdiv):
     """Three CPU figures on this box's own cores: the reference's all-pairs algorithm on
     a bounded sample of the workload (`value`), the same UNIFORM-GRID algorithm as the GPU path on the
@@ -687,6 +711,7 @@ def cpu_baselines(host, p, subdiv):
         "value": n / dtg, "unit": UNIT, "cores": threads, "steps": 1, "seconds": round(dtg, 2),
         "what": f"oracle_step_grid (cell = h/{subdiv}, the GPU path's neighbour search restated in C + OpenMP) over all {n} particles"}
     del G
+    out["reference_shaders_egl"] = egl_reference_run()
     P = O.make_block(10, 100, 10)
     qd = O.default_params()
     O.step(P, qd, 3)

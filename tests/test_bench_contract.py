@@ -35,3 +35,19 @@ def test_product_arm_fails_loudly_without_a_gpu():
     r = _run("--steps", "1", "--warmup", "1", "--no-cpu-baseline")
     assert r.returncode != 0
     assert "cuda" in (r.stderr + r.stdout).lower()
+
+
+def test_egl_reference_runner_builds_and_reports_a_missing_gl_stack(tmp_path):
+    """tools/egl_shader_runner.c (the reference's unmodified shaders, headless): plain
+    C99 without GL headers; on a machine without libEGL it must say so and exit 3 (what bench.py
+    records under cpu_baseline.reference_shaders_egl)."""
+    exe = str(tmp_path / "egl_shader_runner")
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-Wall", "-Wextra", "-Werror",
+                           os.path.join(ROOT, "tools", "egl_shader_runner.c"), "-o", exe, "-ldl"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+    r = subprocess.run([exe, str(tmp_path), "1"], capture_output=True, text=True)
+    if r.returncode == 3:
+        assert "EGL unavailable" in r.stderr
+    else:                                   # a GL-capable machine: the empty directory has no shaders
+        assert r.returncode == 2 and "cannot read" in r.stderr
