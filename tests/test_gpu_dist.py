@@ -156,7 +156,7 @@ def test_rebalancing_moves_slab_faces_and_keeps_parity(sph, oracle):
     ref.scene_block(nx, ny, nz, 0.005, None, 3e-4, 5)
     ref.set_paused(False)
     runs = {}
-    for every in (0, 4):
+    for every in (0, 4, -4):             # static, balanced by particle count, balanced by measured time
         grp = SlabGroup.local(3, cell_subdiv=2, rebalance_every=every)
         grp.apply_params(p)
         grp.scene_block(nx, ny, nz, 0.005, None, 3e-4, 5)
@@ -179,9 +179,10 @@ def test_rebalancing_moves_slab_faces_and_keeps_parity(sph, oracle):
     moves = sum(int(runs[4].info(w).rebalanced) for w in range(3))
     print(f"\n[dist] own particles per rank after 160 steps: static {own[0]} faces {faces[0]}; "
           f"re-balanced {own[4]} faces {faces[4]} ({moves} face moves)")
-    assert sum(own[0]) == n and sum(own[4]) == n
+    assert all(sum(o) == n for o in own.values())
     assert moves > 0 and faces[4] != faces[0]
-    assert all(faces[4][w][1] == faces[4][w + 1][0] for w in range(2)), "slabs must tile the x axis"
+    for e in faces:                      # (time-based decisions depend on the clock; whatever they were:)
+        assert faces[e][0][0] == 0 and all(faces[e][w][1] == faces[e][w + 1][0] for w in range(2)), "slabs must tile the x axis"
     assert max(own[4]) - min(own[4]) < max(own[0]) - min(own[0]), "re-balancing must even out the ranks"
     for g in runs.values():
         g.close()
