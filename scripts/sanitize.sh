@@ -4,7 +4,7 @@
 set -x
 mkdir -p gpurun_out
 SEL='not million and not sixteen and not long_axis and not nan_onset'
-timeout 2400 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 \
+timeout 2400 compute-sanitizer --tool memcheck --report-api-errors no --error-exitcode 9 --print-limit 20 \
     python -m pytest tests/test_gpu_api.py tests/test_gpu_parity.py tests/test_gpu_dist.py tests/test_gpu_consumer.py \
     -m gpu -q -x -k "$SEL" > gpurun_out/san_memcheck.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/san_memcheck.log
 timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 20 \
