@@ -755,24 +755,45 @@ int step_group(nprsph_ctx** cs, int n, cudaEvent_t* ev = nullptr) {
         const bool fused = !(c->cfg.flags & NPRSPH_FLAG_NO_FUSE) && c->hitmask && records_fit(d->lg.reach, d->cap_total);
         const int nxt = 1 - c->cur;
         const SlabNext sn = slab_next(c, true);
-        if (fused) { rc = reset_counts(c); if (rc) return rc; }
-        auto force_range = [&](uint32_t first, uint32_t count) {
-            if (fused)
+        if (fused) {
+            // The interior range runs on the compute stream.  The two boundary ranges are small grids
+            // whose threads still pay the latency of a whole walk (60-90 us each): queued behind the
+            // interior they added 0.18 ms to the lattice step.  They go to the communication stream,
+            // behind the (v, rho) halo that stream carries, and run concurrently with the interior
+            // range as soon as the ghosts have landed.  All three share one queue of deferred slots,
+            // drained on the compute stream once the boundary ranges are done.
+            rc = reset_counts(c);
+            if (rc) return rc;
+            launch_force_queue_reset(c->hitmask, d->cap_total, d->lg.reach, c->stream);
+            CK(c, cudaEventRecord(d->ev_reset, c->stream));
+            auto fused_range = [&](uint32_t first, uint32_t count, cudaStream_t st) {
                 launch_force_integrate_slab(P, V, c->frc[0], c->cell_start, first, count, d->lg, c->sph, c->hitmask,
                                             d->cap_total, c->pos[nxt], c->vel[nxt], c->keys[0], d->own_off,
-                                            c->colliders, sn, c->stream);
-            else
-                launch_force(P, V, c->frc[0], c->cell_start, first, count, d->lg, c->sph, nullptr, c->hitmask,
-                             d->cap_total, c->stream);
-        };
-        force_range(in0, in1 - in0);
-        for (int q = 0; q < n; q++) CK(c, cudaStreamWaitEvent(c->stream, cs[q]->dist->ev_halo, 0));
-        force_range(d->own_off, in0 - d->own_off);
-        force_range(in1, own_end - in1);
-        if (ev && r == 0) CK(c, cudaEventRecord(ev[4], c->stream));
-        if (fused) {
+                                            c->colliders, sn, st);
+            };
+            fused_range(in0, in1 - in0, c->stream);
+            cudaStream_t bs = d->comm_stream;
+            CK(c, cudaStreamWaitEvent(bs, d->ev_reset, 0));
+            for (int q = 0; q < n; q++)              // LOCAL: a neighbour's receive may sit on ITS stream
+                if (q != r) CK(c, cudaStreamWaitEvent(bs, cs[q]->dist->ev_halo, 0));
+            fused_range(d->own_off, in0 - d->own_off, bs);
+            fused_range(in1, own_end - in1, bs);
+            CK(c, cudaEventRecord(d->ev_bdone, bs));
+            CK(c, cudaStreamWaitEvent(c->stream, d->ev_bdone, 0));
+            launch_force_deferred_slab(P, V, c->frc[0], c->cell_start, d->lg, c->sph, c->hitmask, d->cap_total,
+                                       c->pos[nxt], c->vel[nxt], c->keys[0], d->own_off, c->colliders, sn, c->stream);
+            if (ev && r == 0) CK(c, cudaEventRecord(ev[4], c->stream));
             c->cur = nxt;
         } else {
+            auto force_range = [&](uint32_t first, uint32_t count) {
+                launch_force(P, V, c->frc[0], c->cell_start, first, count, d->lg, c->sph, nullptr, c->hitmask,
+                             d->cap_total, c->stream);
+            };
+            force_range(in0, in1 - in0);
+            for (int q = 0; q < n; q++) CK(c, cudaStreamWaitEvent(c->stream, cs[q]->dist->ev_halo, 0));
+            force_range(d->own_off, in0 - d->own_off);
+            force_range(in1, own_end - in1);
+            if (ev && r == 0) CK(c, cudaEventRecord(ev[4], c->stream));
             rc = reset_counts(c);
             if (rc) return rc;
             if (d->n_own)
@@ -816,6 +837,8 @@ void nprsph::dist_destroy(nprsph_ctx* c) {
     if (d->h_counts) cudaFreeHost(d->h_counts);
     if (d->comm_stream) { cudaStreamSynchronize(d->comm_stream); cudaStreamDestroy(d->comm_stream); }
     if (d->ev_rho) cudaEventDestroy(d->ev_rho);
+    if (d->ev_reset) cudaEventDestroy(d->ev_reset);
+    if (d->ev_bdone) cudaEventDestroy(d->ev_bdone);
     if (d->ev_work0) cudaEventDestroy(d->ev_work0);
     if (d->ev_work1) cudaEventDestroy(d->ev_work1);
     if (d->ev_halo) cudaEventDestroy(d->ev_halo);
@@ -888,6 +911,8 @@ int nprsph_dist_init(nprsph_ctx* c, const nprsph_dist_config* cfg) {
     CK(c, cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
     CK(c, cudaEventCreateWithFlags(&d->ev_rho, cudaEventDisableTiming));
     CK(c, cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&d->ev_reset, cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&d->ev_bdone, cudaEventDisableTiming));
     CK(c, cudaEventCreate(&d->ev_work0));
     CK(c, cudaEventCreate(&d->ev_work1));
     if (cfg->transport == NPRSPH_TRANSPORT_NCCL && cfg->world > 1) {

@@ -12,6 +12,7 @@ struct DistState {
     void* nccl_comm = nullptr;
     cudaStream_t comm_stream = nullptr;   // halo traffic that overlaps the interior force pass
     cudaEvent_t ev_rho = nullptr, ev_halo = nullptr;
+    cudaEvent_t ev_reset = nullptr, ev_bdone = nullptr;   // counters reset / boundary force ranges done
     nprsph_ctx* left = nullptr;        // local transport only
     nprsph_ctx* right = nullptr;
 

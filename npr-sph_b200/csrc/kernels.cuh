@@ -56,6 +56,12 @@ void launch_force_integrate_slab(const float4* posid, const float4* velrho, floa
                                  const SphDev& sp, const uint32_t* records, uint32_t rec_stride,
                                  float4* pos_next, float4* vel_next, uint32_t* keys_next, uint32_t key_base,
                                  const ColliderSet& cs, const SlabNext& sn, cudaStream_t st);
+void launch_force_queue_reset(const uint32_t* records, uint32_t rec_stride, int reach, cudaStream_t st);
+void launch_force_deferred_slab(const float4* posid, const float4* velrho, float4* forcep,
+                                const uint32_t* cell_start, const GridDev& g, const SphDev& sp,
+                                const uint32_t* records, uint32_t rec_stride, float4* pos_next, float4* vel_next,
+                                uint32_t* keys_next, uint32_t key_base, const ColliderSet& cs, const SlabNext& sn,
+                                cudaStream_t st);
 void launch_integrate(float4* posid, float4* velrho, const float4* forcep, uint32_t* keys,
                       uint32_t n, const GridDev& g, const SphDev& sp, const ColliderSet& cs,
                       cudaStream_t st);
