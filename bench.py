@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=256, help="lattice block is side^3 particles per GPU")
     ap.add_argument("--subdiv", type=int, default=0, help="grid cells per smoothing length (0 = automatic: 2 here)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--evolve-steps", type=int, default=2000,
                     help="steps the dam break runs before the timed region (0 = time the standing lattice)")
@@ -537,6 +537,27 @@ def run_ours(args):
         assert 0.0 < moved < 0.1, f"e2e: downloaded positions are not one step away from the uploaded ones ({moved})"
         e2e_note = ("host wall clock around upload_state -> step -> asynchronous download_positions of every step, "
                     "final sync inside; the result of step i leaves while the inputs of step i+1 arrive")
+        # PCIe yard-stick (plain torch copies of the same pinned buffers, both directions at once): the
+        # floor of a step that moves these bytes, whatever the kernels cost
+        d_in = torch.empty(n * 8, dtype=torch.float32, device="cuda")
+        d_out = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        for it in range(2):                 # the first round warms the copy engines up
+            p0.record()
+            s_up.wait_event(p0); s_dn.wait_event(p0)
+            for k in range(4):
+                with torch.cuda.stream(s_up):
+                    d_in[:n * 4].copy_(hin[k % 2][0], non_blocking=True); d_in[n * 4:].copy_(hin[k % 2][1], non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    hout[k % 2].copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s_up); torch.cuda.current_stream().wait_stream(s_dn)
+            p1.record(); torch.cuda.synchronize()
+        pcie_ms = p0.elapsed_time(p1) / 4
+        pcie = {"floor_ms_per_step": round(pcie_ms, 3), "h2d_GBps_with_d2h_running": round(n * 32 / pcie_ms / 1e6, 1),
+                "what": "torch copies of the same pinned buffers (32 B/particle in, 16 B/particle out) on two streams, no kernels"}
+        del d_in, d_out
     else:
         cap = run.cap
         h = [torch.empty(cap * 16, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -564,7 +585,9 @@ def run_ours(args):
     e2e = {"value": n_total * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(sum_over_ranks(h2d) / args.e2e_steps),
            "d2h_bytes_per_step": int(sum_over_ranks(d2h) / args.e2e_steps),
-           "steps": args.e2e_steps, "api": run.api, "timing": e2e_note}
+           "steps": args.e2e_steps, "ms_per_step": round(e2e_ms / args.e2e_steps, 3), "api": run.api, "timing": e2e_note}
+    if world == 1:
+        e2e["pcie"] = pcie
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
