@@ -85,6 +85,9 @@ typedef struct nprsph_config {
 
 #define NPRSPH_FLAG_NO_FUSE 4u           /* nprsph_step runs the force and integrate passes as two
                                             launches instead of the fused one (A/B measurements) */
+#define NPRSPH_FLAG_NO_GRAPH 8u          /* nprsph_step launches its kernels one by one instead of replaying
+                                            the CUDA graph of a step (A/B measurements; the environment
+                                            variable NPRSPH_NO_GRAPH=1 does the same for every context) */
 
 typedef struct nprsph_stats {
     uint64_t num_particles;
@@ -98,6 +101,7 @@ typedef struct nprsph_stats {
     float    smoothing_length;
     int32_t  paused;
     int32_t  cell_subdiv;
+    uint64_t graph_steps;       /* steps of nprsph_step that ran as one CUDA graph launch */
 } nprsph_stats;
 
 /* stage indices for nprsph_profile_step() */

@@ -21,6 +21,7 @@ ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED, ERR_COMM = -1, -2,
 FLAG_COUNT_NEIGHBOURS = 1
 FLAG_NO_HITMASK = 2
 FLAG_NO_FUSE = 4
+FLAG_NO_GRAPH = 8
 DOWNLOAD_ASYNC = 1
 
 STAGES = ("keys", "sort", "cells", "reorder", "rho", "force", "integrate")
@@ -68,7 +69,7 @@ class Stats(C.Structure):
                 ("grid_dim", C.c_uint32 * 3), ("key_bits", C.c_uint32),
                 ("sort_passes", C.c_uint32), ("cell_size", C.c_float),
                 ("smoothing_length", C.c_float), ("paused", C.c_int32),
-                ("cell_subdiv", C.c_int32)]
+                ("cell_subdiv", C.c_int32), ("graph_steps", C.c_uint64)]
 
 
 # every symbol include/nprsph.h declares: name -> (restype, argtypes)

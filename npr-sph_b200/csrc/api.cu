@@ -428,6 +428,10 @@ int nprsph_create(const nprsph_config* cfg, nprsph_ctx** out) {
     nprsph_ctx* c = new (std::nothrow) nprsph_ctx();
     if (!c) return fail(nullptr, NPRSPH_ERR_NOMEM, "out of host memory%s");
     c->cfg = *cfg;
+    {
+        const char* off = getenv("NPRSPH_NO_GRAPH");
+        c->graph_off = (cfg->flags & NPRSPH_FLAG_NO_GRAPH) || (off && off[0] && off[0] != '0');
+    }
     c->num_sms = prop.multiProcessorCount;
     // ConstantsData / BoundaryData defaults, Main.cpp:110-122
     c->consts = {0.02f, 4.0f, 3000.0f, 1000.0f};
@@ -458,6 +462,7 @@ int nprsph_destroy(nprsph_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->gl_res) cudaGraphicsUnregisterResource(c->gl_res);
+    if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
     if (c->dist) dist_destroy(c);
     if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
     if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); }
@@ -771,13 +776,86 @@ static int step_once(nprsph_ctx* c) {
     return NPRSPH_OK;
 }
 
+// ---- a step as ONE graph launch ------------------------------------------------------------------------
+// The reference's own scene is 10,000 particles: its step is ~15 kernels of 3-7 us each, i.e. bound by
+// launch overhead, not by the GPU.  Once two consecutive steps were launched with identical parameters
+// (same buffers, grid, constants, colliders, validity flags -- StepSig), the next one is recorded with
+// stream capture and later steps replay the graph until anything in the signature changes.  The
+// kernels and their order are exactly those of step_once, so results are bit-identical.
+static void fill_sig(const nprsph_ctx* c, nprsph_ctx::StepSig& s) {
+    memset(&s, 0, sizeof s);
+    s.n = c->n; s.cap = c->cap;
+    s.cur = c->cur; s.key_bits = c->key_bits; s.num_sms = c->num_sms;
+    s.flags = c->cfg.flags;
+    s.keys_valid = c->keys_valid; s.grid_valid = c->grid_valid; s.mask_valid = c->mask_valid;
+    s.hitmask_words = c->hitmask_words;
+    const void* p[18] = {c->aos, c->pos[0], c->pos[1], c->vel[0], c->vel[1], c->frc[0], c->frc[1],
+                         c->keys[0], c->keys[1], c->vals[0], c->vals[1], c->counts_rho, c->counts_force,
+                         c->sort_ws, c->hitmask, c->cell_start, c->gap_list, c->gap_count};
+    memcpy(s.ptr, p, sizeof p);
+    memcpy(&s.grid, &c->grid, sizeof s.grid);
+    memcpy(&s.sph, &c->sph, sizeof s.sph);
+    memcpy(&s.colliders, &c->colliders, sizeof s.colliders);
+}
+
+static int step_any(nprsph_ctx* c) {
+    if (c->graph_off) return step_once(c);
+    int rc = refresh_params(c);                    // the signature must see THIS step's parameters
+    if (rc) return rc;
+    nprsph_ctx::StepSig sig;
+    fill_sig(c, sig);
+    if (c->step_graph && memcmp(&sig, &c->graph_sig, sizeof sig) == 0) {
+        CK(c, cudaGraphLaunch(c->step_graph, c->stream));
+        const nprsph_ctx::StepPost& p = c->graph_post;
+        c->cur = p.cur; c->keys_valid = p.keys_valid; c->grid_valid = p.grid_valid; c->mask_valid = p.mask_valid;
+        c->aos_stale = p.aos_stale; c->sorted_keys = p.sorted_keys; c->last_perm = p.last_perm;
+        c->steps_done++;
+        c->graph_steps++;
+        return NPRSPH_OK;
+    }
+    if (!(c->plain_sig_valid && memcmp(&sig, &c->plain_sig, sizeof sig) == 0)) {
+        c->plain_sig = sig;                        // first step with these parameters: plain launches
+        c->plain_sig_valid = true;
+        return step_once(c);
+    }
+    // second step in a row with these parameters: record it, then run the recording
+    if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; }
+    const nprsph_ctx::StepPost before = {c->cur, c->keys_valid, c->grid_valid, c->mask_valid, c->aos_stale, c->sorted_keys, c->last_perm};
+    const uint64_t steps_before = c->steps_done;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        rc = step_once(c);
+        const cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+        e = rc ? cudaErrorUnknown : e2;
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&c->step_graph, g, 0);
+        if (g) cudaGraphDestroy(g);
+    }
+    if (e != cudaSuccess) {
+        // nothing ran: put the host-side state back, give graphs up for this context, step plainly
+        cudaGetLastError();
+        c->step_graph = nullptr;
+        c->graph_off = true;
+        c->cur = before.cur; c->keys_valid = before.keys_valid; c->grid_valid = before.grid_valid;
+        c->mask_valid = before.mask_valid; c->aos_stale = before.aos_stale;
+        c->sorted_keys = before.sorted_keys; c->last_perm = before.last_perm;
+        c->steps_done = steps_before;
+        return step_once(c);
+    }
+    c->graph_sig = sig;
+    c->graph_post = {c->cur, c->keys_valid, c->grid_valid, c->mask_valid, c->aos_stale, c->sorted_keys, c->last_perm};
+    CK(c, cudaGraphLaunch(c->step_graph, c->stream));
+    c->graph_steps++;
+    return NPRSPH_OK;
+}
+
 int nprsph_step(nprsph_ctx* c, int n_steps) {
     GUARD(c);
     SINGLE_ONLY(c);
     if (n_steps < 0) return fail(c, NPRSPH_ERR_INVALID, "negative step count%s");
     if (c->paused || c->n == 0) return NPRSPH_OK;  // if (simulate) ..., Main.cpp:293
     for (int s = 0; s < n_steps; s++) {
-        int rc = step_once(c);
+        int rc = step_any(c);
         if (rc) return rc;
     }
     CK(c, cudaGetLastError());
@@ -850,6 +928,7 @@ int nprsph_get_stats(nprsph_ctx* c, nprsph_stats* out) {
     out->smoothing_length = c->sph.h;
     out->paused = c->paused ? 1 : 0;
     out->cell_subdiv = effective_subdiv(c);
+    out->graph_steps = c->graph_steps;
     return NPRSPH_OK;
 }
 

@@ -74,6 +74,28 @@ struct nprsph_ctx {
     int stage_cur = 0;
     bool d2h_pending = false;
 
+    // nprsph_step as one CUDA graph launch (api.cu: step_any).  A step is a fixed sequence of ~15
+    // launches whose arguments only change when the caller changes something; StepSig is everything
+    // those arguments are made of, StepPost the host-side state a step leaves behind.
+    struct StepSig {
+        uint64_t n, cap;
+        int cur, key_bits, num_sms;
+        uint32_t flags;
+        int keys_valid, grid_valid, mask_valid;
+        size_t hitmask_words;
+        const void* ptr[18];
+        nprsph::GridDev grid;
+        nprsph::SphDev sph;
+        nprsph::ColliderSet colliders;
+    };
+    struct StepPost { int cur; bool keys_valid, grid_valid, mask_valid, aos_stale; uint32_t* sorted_keys; uint32_t* last_perm; };
+    cudaGraphExec_t step_graph = nullptr;
+    StepSig graph_sig, plain_sig;       // launch parameters of the recorded step / of the last plain step
+    StepPost graph_post;
+    bool plain_sig_valid = false;
+    bool graph_off = false;             // NPRSPH_FLAG_NO_GRAPH, NPRSPH_NO_GRAPH=1, or a capture that failed
+    uint64_t graph_steps = 0;
+
     nprsph::DistState* dist = nullptr;   // non-null once nprsph_dist_init() succeeded
 };
 

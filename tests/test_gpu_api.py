@@ -258,6 +258,48 @@ def test_fused_force_integrate_step_is_bit_identical_to_the_three_pass_step(sph,
     assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
 
 
+def test_graph_replayed_steps_are_bit_identical_to_plain_launches(sph, oracle):
+    """nprsph_step records the launch sequence of a step as a CUDA graph once two steps in a row had the
+    same parameters and replays it until something changes.  Same kernels, same arguments: a context
+    with NPRSPH_FLAG_NO_GRAPH must produce the same bits -- across a slider edit (new constants: the
+    recording is stale), a state upload (keys stale: one more kernel in the sequence), a collider
+    edit (a by-value kernel argument) and a pass-level call in between."""
+    nx = 18
+    p = oracle.dam_break_params(nx, nx, nx)
+    P = oracle.jitter(oracle.make_block(nx, nx, nx), 0.2 * 0.005, seed=5)
+    sims = []
+    for flags in (0, sph.FLAG_NO_GRAPH):
+        sim = sph.Simulation(cell_subdiv=2, flags=flags)
+        sim.apply_params(p)
+        sim.upload(P)
+        sim.set_paused(False)
+        sims.append(sim)
+
+    def both(f):
+        for s in sims:
+            f(s)
+
+    def same(what):
+        a, b = sims[0].download(), sims[1].download()
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), what
+
+    both(lambda s: s.step(12)); same("steady replay")
+    g0 = sims[0].stats().graph_steps
+    assert g0 >= 9 and sims[1].stats().graph_steps == 0
+    both(lambda s: s.set_slider(2, 2500.0)); both(lambda s: s.step(6)); same("after a slider edit")
+    both(lambda s: s.step(1)); both(lambda s: s.step(1)); both(lambda s: s.step(1)); same("single steps")
+    both(lambda s: s.set_colliders([("sphere", (0.05, 0.0, 0.05), 0.02)]))
+    both(lambda s: s.step(6)); same("after a collider edit")
+    A = sims[0].download()
+    pos4 = np.ascontiguousarray(A[:, 0:4]); vel4 = np.ascontiguousarray(A[:, 4:8])
+    for k in range(4):                                   # upload -> step(1), the streaming pattern
+        both(lambda s: s.upload_state(pos4, vel4)); both(lambda s: s.step(1))
+    same("upload_state + step")
+    both(lambda s: s.pass_rho()); both(lambda s: s.step(5)); same("after a pass-level call")
+    assert sims[0].stats().graph_steps > g0 + 10 and sims[1].stats().graph_steps == 0
+    assert sims[0].stats().steps_done == sims[1].stats().steps_done
+
+
 @pytest.mark.parametrize("coeff", [3.0, 4.0])
 def test_dense_clump_overflows_the_hitmask_gracefully(sph, oracle, coeff):
     """More candidates per column than a record's hit bits hold.  h = 3 lattice spacings on cells of
