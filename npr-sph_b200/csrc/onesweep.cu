@@ -98,8 +98,8 @@ k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, DigitPlan plan, uint
     }
 }
 
-// exclusive scan of one value per thread over a 256-thread CTA
-__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp_tot /*[8]*/) {
+// exclusive scan of one value per thread over the CTA (SORT_WARPS warps)
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp_tot /*[SORT_WARPS]*/) {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     uint32_t incl = v;
 #pragma unroll
@@ -127,8 +127,8 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
            uint32_t mask, const uint32_t* __restrict__ hist, uint32_t* __restrict__ tile_counter,
            volatile uint32_t* __restrict__ status) {
     constexpr int RDX = 1 << BITS;
-    constexpr int DPT = RDX / SORT_THREADS;
-    static_assert(SORT_WARPS * RDX <= SORT_TILE, "warp histograms must fit the value staging area");
+    constexpr int DPT = RDX >= SORT_THREADS ? RDX / SORT_THREADS : 1;     // digits a thread owns in the scan / look-back
+    static_assert(SORT_WARPS * RDX <= 2 * SORT_TILE, "warp histograms must fit the staging area");
     // [0, TILE): staged keys.  [TILE, 2*TILE): the per-warp digit counters while ranking, then the
     // staged values (every read of the counters is finished before the first value is staged).
     __shared__ uint32_t s_buf[2 * SORT_TILE];
@@ -138,7 +138,10 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     __shared__ uint32_t s_tile;
     uint32_t* s_keys = s_buf;
     uint32_t* s_vals = s_buf + SORT_TILE;
-    uint32_t* s_warp_hist = s_buf + SORT_TILE;              // [SORT_WARPS][RDX]
+    // [SORT_WARPS][RDX]; with 16 warps and 512 digits it takes both halves (the keys are staged after
+    // the last read of the counters, too)
+    uint32_t* s_warp_hist = s_buf + (SORT_WARPS * RDX <= SORT_TILE ? SORT_TILE : 0);
+    const bool owner = (int)threadIdx.x * DPT < RDX;        // 512 threads, 256 digits: the upper half owns none
 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
@@ -215,15 +218,18 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     for (int q = 0; q < DPT; q++) {
         const uint32_t d_own = tid * DPT + q;
         uint32_t tc = 0;
+        tile_count[q] = 0; hist_own[q] = 0;
+        if (owner) {
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) {
-            const uint32_t c = s_warp_hist[w * RDX + d_own];
-            s_warp_hist[w * RDX + d_own] = tc;
-            tc += c;
+            for (int w = 0; w < SORT_WARPS; w++) {
+                const uint32_t c = s_warp_hist[w * RDX + d_own];
+                s_warp_hist[w * RDX + d_own] = tc;
+                tc += c;
+            }
+            tile_count[q] = tc;
+            status[(uint64_t)tile * RDX + d_own] = tc | (tile == 0 ? FLAG_INCL : FLAG_AGG);
+            hist_own[q] = hist[d_own];
         }
-        tile_count[q] = tc;
-        status[(uint64_t)tile * RDX + d_own] = tc | (tile == 0 ? FLAG_INCL : FLAG_AGG);
-        hist_own[q] = hist[d_own];
         sum_tc += tc; sum_h += hist_own[q];
     }
     uint32_t global_excl = block_excl_scan_256(sum_h, s_scan);
@@ -235,7 +241,7 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     // kernel's stall samples when it read one status word at a time).
     constexpr int LOOK = 8;
     uint32_t excl[DPT];
-    if (tile > 0) {
+    if (tile > 0 && owner) {
 #pragma unroll
         for (int q = 0; q < DPT; q++) {
             const uint32_t d_own = tid * DPT + q;
@@ -265,6 +271,7 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     }
 #pragma unroll
     for (int q = 0; q < DPT; q++) {
+        if (!owner) break;
         const uint32_t d_own = tid * DPT + q;
         s_out_base[d_own] = global_excl + excl[q] - local_off;
         s_local_off[d_own] = local_off;

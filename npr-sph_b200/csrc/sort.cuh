@@ -7,10 +7,13 @@
 namespace nprsph {
 
 constexpr int SORT_MAX_RADIX = 512;                    // 8-bit digits, or 9-bit when that saves a pass
-constexpr int SORT_THREADS = 256;
+#ifndef NPRSPH_SORT_THREADS
+#define NPRSPH_SORT_THREADS 256
+#endif
+constexpr int SORT_THREADS = NPRSPH_SORT_THREADS;      // 256 (16 pairs per thread) or 512 (8 pairs per thread)
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 4096 pairs per CTA
+constexpr int SORT_TILE = 4096;                        // pairs per CTA
+constexpr int SORT_ITEMS = SORT_TILE / SORT_THREADS;
 constexpr int SORT_MAX_PASSES = 4;
 
 size_t sort_workspace_bytes(uint64_t n);
