@@ -262,7 +262,8 @@ class SlabRunner:
         self.parallelism = (f"{world} slabs along x, 1 process/GPU, ghost halo (pos; v,rho) + migration "
                             f"via ncclSend/ncclRecv each step, faces re-balanced every {args.rebalance_every} steps "
                             f"by {'density-pass time' if args.balance == 'time' else 'particle count'}")
-        self.api = "nprsph_dist_upload + nprsph_dist_step(1) + nprsph_dist_download, pinned host buffers"
+        self.api = ("nprsph_dist_upload_state (pos+vel, 32 B/particle) + nprsph_dist_step(1) + "
+                    "nprsph_dist_download_positions (16 B/particle), pinned host buffers, every rank its own particles")
 
     def step(self, k):
         self.grp.step(k)
@@ -559,18 +560,26 @@ def run_ours(args):
                 "what": "torch copies of the same pinned buffers (32 B/particle in, 16 B/particle out) on two streams, no kernels"}
         del d_in, d_out
     else:
+        # slab mode: the same streaming pattern through nprsph_dist_upload_state / _download_positions
+        # (pos4 = x, y, z, id bits; 32 B in and 16 B out per particle); every step starts from the same
+        # uploaded state, as at N = 1
         cap = run.cap
-        h = [torch.empty(cap * 16, dtype=torch.float32).pin_memory() for _ in range(2)]
-        hid = [torch.empty(cap, dtype=torch.int32).pin_memory() for _ in range(2)]
-        state = {"n": run.grp.download_ptr(0, h[0].data_ptr(), hid[0].data_ptr(), cap)}
+        rec0 = torch.empty(cap * 16, dtype=torch.float32).pin_memory()
+        ids0 = torch.empty(cap, dtype=torch.int32).pin_memory()
+        n0 = run.grp.download_ptr(0, rec0.data_ptr(), ids0.data_ptr(), cap)
+        hp = torch.empty(n0 * 4, dtype=torch.float32).pin_memory()
+        hv = torch.empty(n0 * 4, dtype=torch.float32).pin_memory()
+        r0 = rec0.view(cap, 16)[:n0]
+        hp.view(n0, 4).copy_(r0[:, 0:4]); hp.view(n0, 4)[:, 3] = ids0[:n0].view(torch.float32)
+        hv.view(n0, 4).copy_(r0[:, 4:8])
+        del rec0, ids0, r0
+        hout = [torch.empty(cap * 4, dtype=torch.float32).pin_memory() for _ in range(2)]
 
         def e2e_step(i):
-            a, b = i % 2, (i + 1) % 2
-            n_in = state["n"]
-            run.grp.upload_ptr(0, h[a].data_ptr(), hid[a].data_ptr(), n_in)
+            run.grp.upload_state_ptr(0, hp.data_ptr(), hv.data_ptr(), n0)
             run.grp.step(1)
-            state["n"] = run.grp.download_ptr(0, h[b].data_ptr(), hid[b].data_ptr(), cap)
-            return n_in * 68, state["n"] * 68
+            n_out = run.grp.download_positions_ptr(0, hout[i % 2].data_ptr(), cap)
+            return n0 * 32, n_out * 16
         e2e_step(0)
         barrier()
         t0 = time.perf_counter()
@@ -580,7 +589,8 @@ def run_ours(args):
             h2d, d2h = h2d + a, d2h + b
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
-        e2e_note = "host wall clock, upload -> step -> download of every rank's records, barrier on both sides"
+        e2e_note = ("host wall clock, upload_state -> step -> download_positions of every rank's own particles "
+                    "(synchronous), barrier on both sides")
     e2e_ms = max_over_ranks(e2e_ms)
     e2e = {"value": n_total * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(sum_over_ranks(h2d) / args.e2e_steps),
@@ -597,7 +607,7 @@ def run_ours(args):
     if world == 1:
         del host, hin, hout, rec
     else:
-        del h, hid
+        del hp, hv, hout
     torch.cuda.empty_cache()
 
     # ---- BASELINE configs[3] (64 Mi strong scaling) and configs[4] (32 Mi per GPU weak scaling) ----

@@ -319,6 +319,16 @@ int nprsph_dist_download(nprsph_ctx** ranks, int n_local, int which, nprsph_part
 /* replaces the own particles of this rank by host records + global indices (restart / e2e);
  * a record whose position lies in the slab next door is handed over by the next step */
 int nprsph_dist_upload(nprsph_ctx* ctx, const nprsph_particle* records, const uint32_t* ids, uint64_t n);
+/* Slab-mode counterparts of nprsph_upload_state / nprsph_download_positions (the per-step traffic
+ * of a host application: 32 B in, 16 B out per particle instead of two 68-byte records), in the
+ * slab's own layout: pos4[i] = (x, y, z, bit pattern of the particle's global index),
+ * vel4[i] = (vx, vy, vz, ignored).  upload_state replaces the own particles of this rank like
+ * nprsph_dist_upload (force / density / pressure are outputs of the next step);
+ * download_positions copies the positions of the particles ranks[which] holds, in slot order
+ * (pos4 NULL: only *n_out).  Both are synchronous. */
+int nprsph_dist_upload_state(nprsph_ctx* ctx, const float* pos4, const float* vel4, uint64_t n);
+int nprsph_dist_download_positions(nprsph_ctx** ranks, int n_local, int which, float* pos4,
+                                   uint64_t capacity, uint64_t* n_out);
 /* collective nprsph_profile_step(): SORT = whole prepare phase, REORDER = (v, rho) halo exchange */
 int nprsph_dist_profile_step(nprsph_ctx** ranks, int n_local, int steps, float* stage_ms);
 int nprsph_dist_get_info(nprsph_ctx* ctx, nprsph_dist_info* out);

@@ -280,6 +280,15 @@ k_unpack_records(const float4* __restrict__ rec, const uint32_t* __restrict__ id
     keys[s] = cell_key_slab(p.x, p.y, p.z, g, W, R);
 }
 
+// slab keys of freshly uploaded own particles (nprsph_dist_upload_state)
+__global__ void __launch_bounds__(TPB)
+k_state_keys(const float4* __restrict__ posid, uint32_t n, uint32_t* __restrict__ keys, GridDev g, int W, int R) {
+    const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+    if (s >= n) return;
+    const float4 p = posid[s];
+    keys[s] = cell_key_slab(p.x, p.y, p.z, g, W, R);
+}
+
 // ---- neighbour exchange --------------------------------------------------------------------------
 // Sends sendL/sendR to the left/right rank and receives recvL/recvR from them (byte counts; a
 // rank at the end of the chain has no neighbour on that side).  LOCAL transport: the "ranks" are
@@ -1098,6 +1107,54 @@ int nprsph_dist_upload(nprsph_ctx* c, const nprsph_particle* records, const uint
     d->gather_force = true;          // the uploaded force / pressure columns follow the re-sort
     d->prepared = false;
     d->classified = false;
+    return NPRSPH_OK;
+}
+
+// The per-step traffic of a host application in slab mode: the working arrays already are
+// (x, y, z, id bits) and (vx, vy, vz, rho), so the inputs of a step land straight in the own slots
+// and the positions leave straight from them -- no record packing, 32 + 16 bytes per particle.
+int nprsph_dist_upload_state(nprsph_ctx* c, const float* pos4, const float* vel4, uint64_t n) {
+    GUARD(c);
+    DistState* d = c->dist;
+    if (!d || !d->ready) return fail(c, NPRSPH_ERR_STATE, "distribute a scene first (slab geometry and capacities)%s");
+    if (n > d->cap_own || (n && (!pos4 || !vel4))) return fail(c, NPRSPH_ERR_INVALID, "bad upload%s");
+    const SlabNext sn = slab_next(c, false);
+    if (n) {
+        float4* p = c->pos[c->cur] + d->own_off;
+        CK(c, cudaMemcpyAsync(p, pos4, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(c->vel[c->cur] + d->own_off, vel4, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        k_state_keys<<<blocks_for(n), TPB, 0, c->stream>>>(p, (uint32_t)n, c->keys[0], sn.g, sn.W, sn.R);
+        CK(c, cudaGetLastError());
+    }
+    d->n_own = (uint32_t)n;
+    d->xmax_known = false;
+    d->first_prepare = false;        // a particle of the slab next door is handed over by the next prepare
+    d->gather_force = false;         // force is an output of the next step
+    d->prepared = false;
+    d->classified = false;
+    return NPRSPH_OK;
+}
+
+int nprsph_dist_download_positions(nprsph_ctx** ranks, int n_local, int which, float* pos4,
+                                   uint64_t capacity, uint64_t* n_out) {
+    int rc = check_group(ranks, n_local);
+    if (rc) return rc;
+    if (which < 0 || which >= n_local || !n_out) return NPRSPH_ERR_INVALID;
+    bool fresh = false;              // (see nprsph_dist_download)
+    for (int r = 0; r < n_local; r++) fresh = fresh || ranks[r]->dist->first_prepare;
+    if (fresh) {
+        rc = ensure_prepared(ranks, n_local);
+        if (rc) return rc;
+    }
+    nprsph_ctx* c = ranks[which]; DistState* d = c->dist;
+    CK(c, cudaSetDevice(c->cfg.device));
+    *n_out = d->n_own;
+    if (!pos4) return NPRSPH_OK;
+    if (capacity < d->n_own) return fail(c, NPRSPH_ERR_INVALID, "download buffer too small%s");
+    if (d->n_own)
+        CK(c, cudaMemcpyAsync(pos4, c->pos[c->cur] + d->own_off, (size_t)d->n_own * sizeof(float4),
+                              cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
     return NPRSPH_OK;
 }
 

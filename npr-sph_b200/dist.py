@@ -161,6 +161,30 @@ class SlabGroup:
         s = self.sims[which]
         s._ck(s.lib.nprsph_dist_upload(s._h, rec_ptr, ids_ptr, n))
 
+    def upload_state_ptr(self, which, pos_ptr: int, vel_ptr: int, n: int):
+        """pos4 = (x, y, z, id bits), vel4 = (vx, vy, vz, -): the inputs of a step for local rank `which`."""
+        s = self.sims[which]
+        s._ck(s.lib.nprsph_dist_upload_state(s._h, pos_ptr, vel_ptr, n))
+
+    def upload_state(self, which, pos4: np.ndarray, vel4: np.ndarray):
+        p, v = np.ascontiguousarray(pos4, np.float32), np.ascontiguousarray(vel4, np.float32)
+        assert p.shape == v.shape and p.shape[1] == 4
+        self.upload_state_ptr(which, p.ctypes.data, v.ctypes.data, len(p))
+        self.sims[which].sync()         # the numpy temporaries must outlive the copies
+
+    def download_positions_ptr(self, which, pos_ptr: int, capacity: int) -> int:
+        n = C.c_uint64()
+        self._ck(self.lib.nprsph_dist_download_positions(self._arr, len(self.sims), which, pos_ptr,
+                                                         capacity, C.byref(n)))
+        return n.value
+
+    def download_positions(self, which=0) -> np.ndarray:
+        """(n, 4) float32 of local rank `which`, slot order; column 3 holds the id bits (view as uint32)."""
+        n = self.download_positions_ptr(which, None, 0)
+        out = np.empty((n, 4), np.float32)
+        self.download_positions_ptr(which, out.ctypes.data, n)
+        return out
+
     def profile_step(self, n_steps=1) -> dict:
         ms = (C.c_float * len(B.STAGES))()
         self._ck(self.lib.nprsph_dist_profile_step(self._arr, len(self.sims), n_steps, ms))

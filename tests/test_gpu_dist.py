@@ -198,3 +198,55 @@ def test_slab_scene_rejects_a_jitter_of_a_cell_or_more(sph, oracle):
     grp.scene_block(20, 8, 8, 0.005, None, 0.002, 1)
     assert sum(grp.download(w)[1].size for w in range(2)) == 20 * 8 * 8
     grp.close()
+
+
+def test_slab_streaming_state_in_positions_out(sph, oracle):
+    """nprsph_dist_upload_state / nprsph_dist_download_positions (32 B in, 16 B out per particle) against the
+    record path: a rank that receives (pos, vel, id) and steps must land where the rank that received
+    the full records lands, bit for bit: force, density and pressure are outputs of the step."""
+    from nprsph_b200.dist import SlabGroup
+    nx, ny, nz = 36, 12, 10
+    p = _scene(oracle, nx, ny, nz, gy=-2.0)
+    p.gravity[0] = 300.0
+    grps = []
+    for _ in range(2):
+        g = SlabGroup.local(3, cell_subdiv=2)
+        g.apply_params(p)
+        g.scene_block(nx, ny, nz, 0.005, None, 3e-4, 11)
+        g.set_paused(False)
+        g.step(40)
+        grps.append(g)
+    a, b = grps
+    n = nx * ny * nz
+    moved0 = sum(b.info(w).migrated_total for w in range(3))
+    for rounds in range(3):
+        held = []
+        for w in range(3):
+            rec, ids = a.download(w)
+            pos = b.download_positions(w)
+            assert np.array_equal(pos[:, :3], rec[:, 0:3]) and np.array_equal(pos[:, 3].view(np.uint32), ids)
+            held.append((rec, ids))
+        # the lists hold particles that crossed a face in the last step and are still held by their old
+        # rank: they are handed over by the next step -- through both interfaces
+        for w in range(3):
+            rec, ids = held[w]
+            a.sims[w]._ck(a.lib.nprsph_dist_upload(a.sims[w]._h, np.ascontiguousarray(rec).ctypes.data,
+                                                   np.ascontiguousarray(ids).ctypes.data, len(ids)))
+            a.sims[w].sync()
+            pos4 = np.ascontiguousarray(rec[:, 0:4]); pos4[:, 3] = ids.view(np.float32)
+            b.upload_state(w, pos4, np.ascontiguousarray(rec[:, 4:8]))
+        a.step(7); b.step(7)
+        A, B = a.gather(n), b.gather(n)
+        assert not np.isnan(B[:, POS]).any(), "every particle is owned by exactly one rank"
+        for cols in (POS, VEL, FRC):
+            assert np.array_equal(A[:, cols].view(np.uint32), B[:, cols].view(np.uint32)), (rounds, cols)
+        assert np.array_equal(A[:, 12:14].view(np.uint32), B[:, 12:14].view(np.uint32))
+    assert sum(b.info(w).migrated_total for w in range(3)) > moved0, "scene too static to hand anything over"
+    # error model: more particles than the rank can hold
+    cap = b.info(0).num_own
+    big = np.zeros((10_000_000, 4), np.float32)
+    with pytest.raises(sph.NprSphError):
+        b.upload_state(0, big, big)
+    assert b.info(0).num_own == cap
+    for g in grps:
+        g.close()
