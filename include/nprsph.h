@@ -325,10 +325,13 @@ int nprsph_dist_upload(nprsph_ctx* ctx, const nprsph_particle* records, const ui
  * vel4[i] = (vx, vy, vz, ignored).  upload_state replaces the own particles of this rank like
  * nprsph_dist_upload (force / density / pressure are outputs of the next step);
  * download_positions copies the positions of the particles ranks[which] holds, in slot order
- * (pos4 NULL: only *n_out).  Both are synchronous. */
+ * (pos4 NULL: only *n_out).  Same asynchrony as the single-context pair: the upload travels on a
+ * copy stream into a double-buffered staging area (host buffers valid until the next
+ * nprsph_dist_step returns or nprsph_sync), NPRSPH_DOWNLOAD_ASYNC lets the positions leave on a
+ * third stream while the next step's inputs arrive; nprsph_sync() waits for both. */
 int nprsph_dist_upload_state(nprsph_ctx* ctx, const float* pos4, const float* vel4, uint64_t n);
 int nprsph_dist_download_positions(nprsph_ctx** ranks, int n_local, int which, float* pos4,
-                                   uint64_t capacity, uint64_t* n_out);
+                                   uint64_t capacity, uint64_t* n_out, uint32_t flags);
 /* collective nprsph_profile_step(): SORT = whole prepare phase, REORDER = (v, rho) halo exchange */
 int nprsph_dist_profile_step(nprsph_ctx** ranks, int n_local, int steps, float* stage_ms);
 int nprsph_dist_get_info(nprsph_ctx* ctx, nprsph_dist_info* out);

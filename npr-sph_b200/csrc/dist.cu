@@ -280,12 +280,16 @@ k_unpack_records(const float4* __restrict__ rec, const uint32_t* __restrict__ id
     keys[s] = cell_key_slab(p.x, p.y, p.z, g, W, R);
 }
 
-// slab keys of freshly uploaded own particles (nprsph_dist_upload_state)
+// staged inputs of a step (nprsph_dist_upload_state) -> own slots + slab keys
 __global__ void __launch_bounds__(TPB)
-k_state_keys(const float4* __restrict__ posid, uint32_t n, uint32_t* __restrict__ keys, GridDev g, int W, int R) {
+k_import_state_slab(const float4* __restrict__ spos, const float4* __restrict__ svel, uint32_t n,
+                    float4* __restrict__ posid, float4* __restrict__ velrho, uint32_t* __restrict__ keys,
+                    GridDev g, int W, int R) {
     const uint32_t s = blockIdx.x * TPB + threadIdx.x;
     if (s >= n) return;
-    const float4 p = posid[s];
+    const float4 p = spos[s];
+    posid[s] = p;
+    velrho[s] = svel[s];
     keys[s] = cell_key_slab(p.x, p.y, p.z, g, W, R);
 }
 
@@ -1111,8 +1115,30 @@ int nprsph_dist_upload(nprsph_ctx* c, const nprsph_particle* records, const uint
 }
 
 // The per-step traffic of a host application in slab mode: the working arrays already are
-// (x, y, z, id bits) and (vx, vy, vz, rho), so the inputs of a step land straight in the own slots
-// and the positions leave straight from them -- no record packing, 32 + 16 bytes per particle.
+// (x, y, z, id bits) and (vx, vy, vz, rho), so no record packing -- 32 + 16 bytes per particle.  The
+// streams, events and staging buffers are the context's (api.cu uses the same for the single-GPU pair).
+static int ensure_staging_slab(nprsph_ctx* c) {
+    DistState* d = c->dist;
+    if (!c->h2d_stream) {
+        CK(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        CK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < nprsph_ctx::STAGE_CHUNKS; i++) CK(c, cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) CK(c, cudaEventCreateWithFlags(&c->ev_imported[i], cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_published, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
+    }
+    if (c->stage_cap < d->cap_own) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaStreamSynchronize(c->h2d_stream));
+        CK(c, cudaStreamSynchronize(c->d2h_stream));
+        c->stage_cap = 0;
+        for (int i = 0; i < 2; i++) CK(c, realloc_dev(c->stage_in[i], 2 * (size_t)d->cap_own));
+        CK(c, realloc_dev(c->stage_pos, (size_t)d->cap_own));
+        c->stage_cap = d->cap_own;
+    }
+    return NPRSPH_OK;
+}
+
 int nprsph_dist_upload_state(nprsph_ctx* c, const float* pos4, const float* vel4, uint64_t n) {
     GUARD(c);
     DistState* d = c->dist;
@@ -1120,10 +1146,29 @@ int nprsph_dist_upload_state(nprsph_ctx* c, const float* pos4, const float* vel4
     if (n > d->cap_own || (n && (!pos4 || !vel4))) return fail(c, NPRSPH_ERR_INVALID, "bad upload%s");
     const SlabNext sn = slab_next(c, false);
     if (n) {
-        float4* p = c->pos[c->cur] + d->own_off;
-        CK(c, cudaMemcpyAsync(p, pos4, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-        CK(c, cudaMemcpyAsync(c->vel[c->cur] + d->own_off, vel4, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-        k_state_keys<<<blocks_for(n), TPB, 0, c->stream>>>(p, (uint32_t)n, c->keys[0], sn.g, sn.W, sn.R);
+        int rc = ensure_staging_slab(c);
+        if (rc) return rc;
+        // the copy stream brings the chunks in -- while the previous step still computes -- and the
+        // compute stream moves each into the own slots as it lands
+        const int b = c->stage_cur;
+        c->stage_cur ^= 1;
+        float4* sp = c->stage_in[b];
+        float4* sv = sp + d->cap_own;
+        CK(c, cudaStreamWaitEvent(c->h2d_stream, c->ev_imported[b], 0));     // its last import has read the buffer
+        const uint64_t per = (n + nprsph_ctx::STAGE_CHUNKS - 1) / nprsph_ctx::STAGE_CHUNKS;
+        for (int k = 0; k < nprsph_ctx::STAGE_CHUNKS; k++) {
+            const uint64_t first = (uint64_t)k * per;
+            if (first >= n) break;
+            const uint64_t cnt = n - first < per ? n - first : per;
+            CK(c, cudaMemcpyAsync(sp + first, pos4 + 4 * first, cnt * sizeof(float4), cudaMemcpyHostToDevice, c->h2d_stream));
+            CK(c, cudaMemcpyAsync(sv + first, vel4 + 4 * first, cnt * sizeof(float4), cudaMemcpyHostToDevice, c->h2d_stream));
+            CK(c, cudaEventRecord(c->ev_chunk[k], c->h2d_stream));
+            CK(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0));
+            k_import_state_slab<<<blocks_for(cnt), TPB, 0, c->stream>>>(
+                sp + first, sv + first, (uint32_t)cnt, c->pos[c->cur] + d->own_off + first,
+                c->vel[c->cur] + d->own_off + first, c->keys[0] + first, sn.g, sn.W, sn.R);
+        }
+        CK(c, cudaEventRecord(c->ev_imported[b], c->stream));
         CK(c, cudaGetLastError());
     }
     d->n_own = (uint32_t)n;
@@ -1136,7 +1181,7 @@ int nprsph_dist_upload_state(nprsph_ctx* c, const float* pos4, const float* vel4
 }
 
 int nprsph_dist_download_positions(nprsph_ctx** ranks, int n_local, int which, float* pos4,
-                                   uint64_t capacity, uint64_t* n_out) {
+                                   uint64_t capacity, uint64_t* n_out, uint32_t flags) {
     int rc = check_group(ranks, n_local);
     if (rc) return rc;
     if (which < 0 || which >= n_local || !n_out) return NPRSPH_ERR_INVALID;
@@ -1151,10 +1196,22 @@ int nprsph_dist_download_positions(nprsph_ctx** ranks, int n_local, int which, f
     *n_out = d->n_own;
     if (!pos4) return NPRSPH_OK;
     if (capacity < d->n_own) return fail(c, NPRSPH_ERR_INVALID, "download buffer too small%s");
-    if (d->n_own)
-        CK(c, cudaMemcpyAsync(pos4, c->pos[c->cur] + d->own_off, (size_t)d->n_own * sizeof(float4),
-                              cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
+    if (!d->n_own) return NPRSPH_OK;
+    rc = ensure_staging_slab(c);
+    if (rc) return rc;
+    // a copy of the own positions, so that the next step may overwrite the slots while they travel
+    if (c->d2h_pending) CK(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));    // the previous copy has left the staging buffer
+    CK(c, cudaMemcpyAsync(c->stage_pos, c->pos[c->cur] + d->own_off, (size_t)d->n_own * sizeof(float4),
+                          cudaMemcpyDeviceToDevice, c->stream));
+    CK(c, cudaEventRecord(c->ev_published, c->stream));
+    CK(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_published, 0));
+    CK(c, cudaMemcpyAsync(pos4, c->stage_pos, (size_t)d->n_own * sizeof(float4), cudaMemcpyDeviceToHost, c->d2h_stream));
+    CK(c, cudaEventRecord(c->ev_copied, c->d2h_stream));
+    c->d2h_pending = true;
+    if (!(flags & NPRSPH_DOWNLOAD_ASYNC)) {
+        CK(c, cudaStreamSynchronize(c->d2h_stream));
+        c->d2h_pending = false;
+    }
     return NPRSPH_OK;
 }
 

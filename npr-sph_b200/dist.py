@@ -172,10 +172,11 @@ class SlabGroup:
         self.upload_state_ptr(which, p.ctypes.data, v.ctypes.data, len(p))
         self.sims[which].sync()         # the numpy temporaries must outlive the copies
 
-    def download_positions_ptr(self, which, pos_ptr: int, capacity: int) -> int:
+    def download_positions_ptr(self, which, pos_ptr: int, capacity: int, asynchronous: bool = False) -> int:
+        """asynchronous: returns at once; sync() (or the next synchronous download) waits for the copy."""
         n = C.c_uint64()
         self._ck(self.lib.nprsph_dist_download_positions(self._arr, len(self.sims), which, pos_ptr,
-                                                         capacity, C.byref(n)))
+                                                         capacity, C.byref(n), 1 if asynchronous else 0))
         return n.value
 
     def download_positions(self, which=0) -> np.ndarray:

@@ -223,7 +223,12 @@ def test_slab_streaming_state_in_positions_out(sph, oracle):
         held = []
         for w in range(3):
             rec, ids = a.download(w)
-            pos = b.download_positions(w)
+            if rounds == 1:                              # asynchronous: lands by the next sync()
+                pos = np.empty((len(ids), 4), np.float32)
+                assert b.download_positions_ptr(w, pos.ctypes.data, len(ids), asynchronous=True) == len(ids)
+                b.sync()
+            else:
+                pos = b.download_positions(w)
             assert np.array_equal(pos[:, :3], rec[:, 0:3]) and np.array_equal(pos[:, 3].view(np.uint32), ids)
             held.append((rec, ids))
         # the lists hold particles that crossed a face in the last step and are still held by their old
