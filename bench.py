@@ -564,6 +564,7 @@ def run_ours(args):
         # (pos4 = x, y, z, id bits; 32 B in and 16 B out per particle); every step starts from the same
         # uploaded state, as at N = 1
         cap = run.cap
+        run.grp.freeze_faces(True)          # the same lists are uploaded every step: the faces must stay put
         rec0 = torch.empty(cap * 16, dtype=torch.float32).pin_memory()
         ids0 = torch.empty(cap, dtype=torch.int32).pin_memory()
         n0 = run.grp.download_ptr(0, rec0.data_ptr(), ids0.data_ptr(), cap)
@@ -812,5 +813,16 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
-    else:
+    elif int(os.environ.get("WORLD_SIZE", "1")) <= 1:
         run_ours(a)
+    else:
+        # One rank failing must end the job, not hang it: the ordinary interpreter shutdown would wait in
+        # nprsph_destroy for collectives whose peers never arrive, and torchrun only tears the other
+        # ranks down once this process is gone.
+        try:
+            run_ours(a)
+        except BaseException:
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush(); sys.stdout.flush()
+            os._exit(1)

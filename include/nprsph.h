@@ -332,6 +332,10 @@ int nprsph_dist_upload(nprsph_ctx* ctx, const nprsph_particle* records, const ui
 int nprsph_dist_upload_state(nprsph_ctx* ctx, const float* pos4, const float* vel4, uint64_t n);
 int nprsph_dist_download_positions(nprsph_ctx** ranks, int n_local, int which, float* pos4,
                                    uint64_t capacity, uint64_t* n_out, uint32_t flags);
+/* frozen != 0: no further re-balancing decisions (a move already decided still takes effect at the
+ * next step).  For hosts that upload the same particle lists again and again: an uploaded particle may
+ * lie at most `reach` cell layers beyond a slab face.  Every rank of the group makes the same call. */
+int nprsph_dist_freeze_faces(nprsph_ctx* ctx, int frozen);
 /* collective nprsph_profile_step(): SORT = whole prepare phase, REORDER = (v, rho) halo exchange */
 int nprsph_dist_profile_step(nprsph_ctx** ranks, int n_local, int steps, float* stage_ms);
 int nprsph_dist_get_info(nprsph_ctx* ctx, nprsph_dist_info* out);

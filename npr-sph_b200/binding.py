@@ -132,6 +132,7 @@ SYMBOLS = {
                                        C.POINTER(C.c_uint64)]),
     "nprsph_dist_upload": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "nprsph_dist_upload_state": (C.c_int, [_P, _P, _P, C.c_uint64]),
+    "nprsph_dist_freeze_faces": (C.c_int, [_P, C.c_int]),
     "nprsph_dist_download_positions": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, C.c_uint64,
                                                  C.POINTER(C.c_uint64), C.c_uint32]),
     "nprsph_dist_profile_step": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.POINTER(C.c_float)]),

@@ -600,7 +600,8 @@ int prepare_group(nprsph_ctx** cs, int n) {
         d->migrated_total += leaveL[r] + leaveR[r];
         d->last_migrated = leaveL[r] + leaveR[r];
         // faces of the prepare after this one (the coming step keys its particles against them)
-        if (d->rebalance_every > 0 && !fp && d->steps_done > 0 && d->steps_done % (uint64_t)d->rebalance_every == 0) {
+        if (d->rebalance_every > 0 && !d->faces_frozen && !fp && d->steps_done > 0 &&
+            d->steps_done % (uint64_t)d->rebalance_every == 0) {
             const int mL = hasL ? face_move(fromL, mine, d->R, d->cap_ghost, d->balance_time) : 0;
             const int mR = hasR ? face_move(mine, fromR, d->R, d->cap_ghost, d->balance_time) : 0;
             d->X0_next = d->X0 + mL;
@@ -1111,6 +1112,18 @@ int nprsph_dist_upload(nprsph_ctx* c, const nprsph_particle* records, const uint
     d->gather_force = true;          // the uploaded force / pressure columns follow the re-sort
     d->prepared = false;
     d->classified = false;
+    return NPRSPH_OK;
+}
+
+// A host that re-uploads the SAME particle lists step after step (a replay, the e2e measurement) must
+// keep the slab faces where they are: every face move shifts one more x layer of those lists into the
+// slab next door, and an uploaded particle may lie at most `reach` layers beyond a face (it is handed
+// over like a leaver, k_unpack_migrants).  Every rank of the group must make the same call (the two
+// ranks of a face decide together).  A move already decided still takes effect at the next step.
+int nprsph_dist_freeze_faces(nprsph_ctx* c, int frozen) {
+    GUARD(c);
+    if (!c->dist) return fail(c, NPRSPH_ERR_STATE, "not a slab rank (nprsph_dist_init)%s");
+    c->dist->faces_frozen = frozen != 0;
     return NPRSPH_OK;
 }
 

@@ -49,6 +49,7 @@ struct DistState {
     bool work_timed = false;
     float cost_ms = 0.f;               // smoothed duration of the density pass (the rank's work per step)
     uint64_t rebalanced = 0;           // face moves so far (both faces of this rank)
+    bool faces_frozen = false;         // nprsph_dist_freeze_faces: no further re-balancing decisions
     uint32_t* mig_ids = nullptr;       // [4][2*cap_mig] scratch: ids, iota, sorted ids, order
     void* mig_sort_ws = nullptr;
 };

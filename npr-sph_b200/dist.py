@@ -161,6 +161,11 @@ class SlabGroup:
         s = self.sims[which]
         s._ck(s.lib.nprsph_dist_upload(s._h, rec_ptr, ids_ptr, n))
 
+    def freeze_faces(self, frozen: bool = True):
+        """No further re-balancing decisions (for hosts that re-upload the same lists every step)."""
+        for s in self.sims:
+            s._ck(s.lib.nprsph_dist_freeze_faces(s._h, 1 if frozen else 0))
+
     def upload_state_ptr(self, which, pos_ptr: int, vel_ptr: int, n: int):
         """pos4 = (x, y, z, id bits), vel4 = (vx, vy, vz, -): the inputs of a step for local rank `which`."""
         s = self.sims[which]
