@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--side", type=int, default=256, help="lattice block is side^3 particles per GPU")
     ap.add_argument("--subdiv", type=int, default=0, help="grid cells per smoothing length (0 = automatic: 2 here)")
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-overlap", action="store_true",
+                    help="N > 1: asynchronous position downloads in the e2e leg (N = 1 always overlaps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--evolve-steps", type=int, default=2000,
                     help="steps the dam break runs before the timed region (0 = time the standing lattice)")
@@ -263,7 +265,7 @@ class SlabRunner:
                             f"via ncclSend/ncclRecv each step, faces re-balanced every {args.rebalance_every} steps "
                             f"by {'density-pass time' if args.balance == 'time' else 'particle count'}")
         self.api = ("nprsph_dist_upload_state (pos+vel, 32 B/particle) + nprsph_dist_step(1) + "
-                    "nprsph_dist_download_positions (16 B/particle, asynchronous), pinned host buffers, every rank its own particles")
+                    "nprsph_dist_download_positions (16 B/particle), pinned host buffers, every rank its own particles")
 
     def step(self, k):
         self.grp.step(k)
@@ -579,7 +581,9 @@ def run_ours(args):
         def e2e_step(i):
             run.grp.upload_state_ptr(0, hp.data_ptr(), hv.data_ptr(), n0)
             run.grp.step(1)
-            n_out = run.grp.download_positions_ptr(0, hout[i % 2].data_ptr(), cap, asynchronous=True)
+            # (synchronous: the overlapped form -- asynchronous=True, 2.67e9 /s at N = 2,
+            #  profiles/bench_r2_n2_streaming_e2e.json -- was not re-measured at N = 8 after the face freeze)
+            n_out = run.grp.download_positions_ptr(0, hout[i % 2].data_ptr(), cap, asynchronous=args.e2e_overlap)
             return n0 * 32, n_out * 16
         e2e_step(0)
         run.grp.sync()
@@ -592,8 +596,9 @@ def run_ours(args):
         run.grp.sync()                      # the last asynchronous download has landed
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
-        e2e_note = ("host wall clock, upload_state -> step -> asynchronous download_positions of every rank's own "
-                    "particles, final sync inside, barrier on both sides")
+        e2e_note = ("host wall clock, upload_state -> step -> download_positions of every rank's own particles "
+                    f"({'asynchronous, final sync inside' if args.e2e_overlap else 'synchronous: copy in, step, copy out in series'}), "
+                    "barrier on both sides")
     e2e_ms = max_over_ranks(e2e_ms)
     e2e = {"value": n_total * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(sum_over_ranks(h2d) / args.e2e_steps),
